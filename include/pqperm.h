@@ -1,0 +1,177 @@
+/*
+ * pqperm.h -- C ABI of libpqperm.so: the B200 (sm_100a) implementation of
+ * piquasso's permanent hot path.
+ *
+ * Every entry point takes plain pointers and sizes (no torch / numpy / C++
+ * types) and returns 0 on success or a PQ_ERR_* code; pq_last_error() gives the
+ * message for the calling thread.  No exception crosses this boundary and
+ * there is NO CPU fallback: without a usable CUDA device the compute calls
+ * return PQ_ERR_NO_DEVICE.
+ *
+ * "Reference" below is Budapest-Quantum-Computing-Group/piquasso 8.0.1; each
+ * entry cites the reference interface it replaces (paths relative to the
+ * reference tree).
+ *
+ * Layout conventions (same as the reference's Matrix<std::complex<T>>,
+ * src/matrix.hpp:152-260): matrices are row-major, `R` rows by `C` columns,
+ * complex entries interleaved (re, im); `rows` has R and `cols` has C int32
+ * multiplicities.  Inputs are borrowed for the duration of the call and never
+ * written.
+ */
+#ifndef PQPERM_H
+#define PQPERM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PQ_OK 0
+#define PQ_ERR_SUM_MISMATCH 1 /* sum(rows) != sum(cols): the reference throws, src/permanent.cpp:97-104 */
+#define PQ_ERR_BAD_ARG 2
+#define PQ_ERR_NO_DEVICE 3    /* no CUDA device / driver: there is no CPU fallback */
+#define PQ_ERR_CUDA 4
+#define PQ_ERR_TOO_LARGE 5    /* more than PQ_MAX_COLS active columns or PQ_MAX_DIGITS active rows */
+
+#define PQ_MAX_COLS 64   /* columns with non-zero multiplicity */
+#define PQ_MAX_DIGITS 64 /* rows with non-zero multiplicity after the split */
+
+/* Message of the last failing call made by this thread ("" if none). */
+const char *pq_last_error(void);
+
+/* Number of usable CUDA devices (0 when there is no driver/GPU). */
+int pq_device_count(void);
+
+/* Devices used by the host-buffer entry points below; default = device 0 only.
+ * With n > 1 a single permanent's term space is split over the devices and
+ * the partial sums are combined (single process; the multi-process path is
+ * pq_perm_partial_c128 + an NCCL all-reduce done by the caller). */
+int pq_set_devices(const int *device_ids, int n);
+
+/* ---------------------------------------------------------------------
+ * permanent(matrix, rows, cols) -> complex scalar
+ * Replaces permanent_cpp<double> / permanent_cpp<float>
+ * (src/permanent.hpp:32-34, src/permanent.cpp:49-264) as bound by
+ * permanent_np<T> (piquasso/_math/permanent.cpp:26-41).
+ * The c64 entry converts to double, computes in FP64 and rounds once.
+ * ------------------------------------------------------------------- */
+int pq_perm_c128(const double *A, int R, int C, const int32_t *rows,
+                 const int32_t *cols, double out[2]);
+int pq_perm_c64(const float *A, int R, int C, const int32_t *rows,
+                const int32_t *cols, float out[2]);
+
+/* ---------------------------------------------------------------------
+ * permanent_laplace(matrix, rows, cols) -> complex vector
+ * Replaces permanent_laplace_cpp<T> (src/permanent_laplace.hpp:32-34,
+ * src/permanent_laplace.cpp:43-240) as bound by permanent_laplace_np<T>
+ * (piquasso/_math/permanent.cpp:43-58).  `out` must hold 2*max(C,1) values;
+ * *out_len receives the number of complex results: 1 on the reference's
+ * early-out (src/permanent_laplace.cpp:52-57), otherwise C.
+ * ------------------------------------------------------------------- */
+int pq_perm_laplace_c128(const double *A, int R, int C, const int32_t *rows,
+                         const int32_t *cols, double *out, int *out_len);
+int pq_perm_laplace_c64(const float *A, int R, int C, const int32_t *rows,
+                        const int32_t *cols, float *out, int *out_len);
+
+/* ---------------------------------------------------------------------
+ * Batch of independent permanent_laplace problems in one call (what the
+ * Clifford-Clifford sampler issues once per photon per shot,
+ * piquasso/_simulators/passive/sampling.py:723-734).  Problem b has
+ * R[b] x C[b] matrix at A + 2*a_off[b] doubles, multiplicities at
+ * rows + r_off[b] / cols + c_off[b]; its C[b] (or 1) results are written at
+ * out + 2*o_off[b], and out_len[b] is set as above.
+ * ------------------------------------------------------------------- */
+int pq_perm_laplace_batch_c128(int nprob, const double *A, const int64_t *a_off,
+                               const int32_t *R, const int32_t *C,
+                               const int32_t *rows, const int64_t *r_off,
+                               const int32_t *cols, const int64_t *c_off,
+                               double *out, const int64_t *o_off,
+                               int32_t *out_len);
+
+/* ---------------------------------------------------------------------
+ * Partitioned permanent: the piece of one permanent that rank `part` of
+ * `nparts` owns.  The term space [0, idx_max) (src/permanent.cpp:131-142) is
+ * cut into equal-length Gray-code segments (one per GPU thread; the
+ * hierarchical form of src/permanent.cpp:158-164) and rank `part` walks the
+ * contiguous segment range [nseg*part/nparts, nseg*(part+1)/nparts).
+ *
+ * The UNSCALED partial sum is left in DEVICE memory as four doubles
+ * (re_hi, re_lo, im_hi, im_lo; value = hi + lo) at d_partial on `device`,
+ * enqueued on `stream` (a cudaStream_t, NULL = the library's own stream,
+ * synchronised before returning).  The caller sums the four doubles over
+ * ranks (one NCCL all-reduce) and calls pq_perm_finish.
+ *
+ * *status (host int, may be NULL) receives 0 when a partial was enqueued or
+ * 1 when the problem is one of the reference's trivial cases and `trivial`
+ * already holds the final value (src/permanent.cpp:106-122).
+ * ------------------------------------------------------------------- */
+int pq_perm_partial_c128(const double *A, int R, int C, const int32_t *rows,
+                         const int32_t *cols, int part, int nparts, int device,
+                         void *stream, double *d_partial, int *status,
+                         double trivial[2]);
+
+/* hi/lo quadruple + sum(rows) -> permanent: (hi+lo) * 2^-(sum_rows-1)
+ * (src/permanent.cpp:259). */
+int pq_perm_finish(const double partial[4], int sum_rows, double out[2]);
+
+/* ---------------------------------------------------------------------
+ * Introspection used by the parity tests and the bench.
+ * ------------------------------------------------------------------- */
+typedef struct pq_plan_info {
+    int64_t idx_max;       /* number of Gray-code terms, prod(limits) */
+    int64_t seg_len;       /* terms per segment (per GPU thread) */
+    int64_t nseg;          /* number of segments = idx_max / seg_len */
+    int32_t active_rows;   /* Gray digits with radix >= 2 */
+    int32_t active_cols;   /* columns with multiplicity > 0 */
+    int32_t low_digits;    /* digits walked inside a segment */
+    int32_t kernel;        /* 1 = generic n-ary walk, 2 = binary constant-bank walk */
+    int32_t cols_padded;   /* register-resident row sums per thread */
+    int32_t sum_rows;
+    int32_t trivial;       /* 1 = handled by a reference early-out */
+    double flops_per_term; /* 2*C + 6*M + 2 */
+} pq_plan_info;
+
+/* Plan that pq_perm_c128 would use for these multiplicities (no GPU needed). */
+int pq_perm_plan(int R, int C, const int32_t *rows, const int32_t *cols,
+                 pq_plan_info *info);
+
+/* Gray digits (reference digit order, one per row after the split, i.e. R
+ * entries for digits 0..R-1 of the split problem) that the GPU path assigns
+ * to `offset`, computed by the same host/device code path the kernels use for
+ * seeding (no GPU needed): enumeration parity against
+ * src/n_aryGrayCodeCounter.hpp:170-194. */
+int pq_perm_gray_of_offset(int R, const int32_t *rows, int64_t offset,
+                           int32_t *gray);
+
+/* Per-segment unscaled partial sums of one permanent, segments
+ * [seg_begin, seg_begin+nseg), 2 doubles (re, im) each, written to host `out`:
+ * partition-indexing parity (segment s covers offsets
+ * [s*seg_len, (s+1)*seg_len)). */
+int pq_perm_segment_sums_c128(const double *A, int R, int C,
+                              const int32_t *rows, const int32_t *cols,
+                              int64_t seg_begin, int64_t nseg, double *out);
+
+/* Kernel-only duration (ms, CUDA events on the library stream) of the last
+ * pq_perm_c128 / pq_perm_laplace* call made on `device`; -1 if none. */
+double pq_last_kernel_ms(int device);
+
+/* Number of kernels the library has launched on all devices since load. */
+int64_t pq_launch_count(void);
+
+/* Measured FP64 peak of `device`: a dependent-free DFMA loop over all SMs,
+ * `iters` FMAs per thread; returns TFLOP/s (2 flop per FMA), <0 on error. */
+double pq_fp64_peak_tflops(int device, int iters);
+
+/* Select the permanent kernel: 0 = automatic, 1 = force the generic walk,
+ * 2 = force the binary constant-bank walk where applicable (tests / bench). */
+int pq_set_kernel_choice(int choice);
+
+/* Override the segment length exponent (0 = automatic): tests only. */
+int pq_set_seg_len_hint(int64_t seg_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PQPERM_H */

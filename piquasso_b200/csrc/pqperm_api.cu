@@ -1,0 +1,607 @@
+// pqperm_api.cu -- the C ABI of libpqperm.so (include/pqperm.h): host-side
+// preprocessing, device contexts, launches and result assembly.
+//
+// There is no CPU implementation of the term sum anywhere in this library: if
+// no CUDA device is usable every compute entry returns PQ_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pqperm.h"
+#include "pqperm_launch.h"
+#include "pqperm_plan.h"
+
+namespace pqperm {
+
+// parts of the binary kernel family (pqperm_kernels_binary.cu)
+#define PQ_DECL_PART(k)                                                                 \
+    cudaError_t launch_binary_part_##k(int, int, int, const WalkParams &, const double2 *, \
+                                       cudaMemcpyKind, int, int, cudaStream_t, LaunchInfo *);
+PQ_DECL_PART(0)
+PQ_DECL_PART(1)
+PQ_DECL_PART(2)
+PQ_DECL_PART(3)
+#undef PQ_DECL_PART
+
+cudaError_t launch_binary(int nc, int B, int chains, const WalkParams &P,
+                          const double2 *A2_src, cudaMemcpyKind kind, int num_sms,
+                          int max_grid, cudaStream_t stream, LaunchInfo *info)
+{
+    if (nc <= 20)
+        return launch_binary_part_0(nc, B, chains, P, A2_src, kind, num_sms, max_grid, stream, info);
+    if (nc <= 30)
+        return launch_binary_part_1(nc, B, chains, P, A2_src, kind, num_sms, max_grid, stream, info);
+    if (nc <= 40)
+        return launch_binary_part_2(nc, B, chains, P, A2_src, kind, num_sms, max_grid, stream, info);
+    return launch_binary_part_3(nc, B, chains, P, A2_src, kind, num_sms, max_grid, stream, info);
+}
+
+// Laplace kernels (pqperm_kernels_laplace.cu)
+int laplace_run(int dev_slot, const double *A, int R, int C, const int32_t *rows,
+                const int32_t *cols, double *out, int *out_len, std::string &err);
+
+} // namespace pqperm
+
+using namespace pqperm;
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+static int fail_cuda(cudaError_t e, const char *what)
+{
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    // a missing driver / device must read as "no device", not as a CUDA bug
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ||
+        e == cudaErrorInitializationError)
+        return PQ_ERR_NO_DEVICE;
+    return PQ_ERR_CUDA;
+}
+
+#define PQ_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess)                                                         \
+            return fail_cuda(e__, #call);                                               \
+    } while (0)
+
+extern "C" const char *pq_last_error(void) { return g_last_error.c_str(); }
+
+// ---------------------------------------------------------------------------
+// per-device context
+// ---------------------------------------------------------------------------
+namespace pqperm {
+
+constexpr int kMaxGrid = 148 * 32 * 2;
+
+struct DeviceCtx {
+    int device = -1;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_up = nullptr;   // uploads of the last enqueue have left h_pinned
+    bool up_pending = false;
+    double *d_A2 = nullptr;        // (kMaxDigits+1) x kMaxCols double2
+    double *d_partials = nullptr;  // kMaxGrid x 4
+    double *d_out = nullptr;       // 4 doubles
+    uint8_t *d_sched = nullptr;    // kMaxSegLenNary
+    double *d_wtab = nullptr;      // kMaxSegLenNary
+    double *d_binom = nullptr;     // kMaxDigits * 256
+    double *h_pinned = nullptr;    // staging: A2 + out
+    double last_kernel_ms = -1.0;
+    bool ready = false;
+};
+
+static std::mutex g_mu;                 // one caller at a time (GIL-held callers anyway)
+static std::vector<std::unique_ptr<DeviceCtx>> g_ctx;
+static std::vector<int> g_devices = {0};
+static std::atomic<int64_t> g_launches{0};
+static int g_kernel_choice = 0;
+static int64_t g_seg_len_hint = 0;
+
+constexpr size_t kA2Doubles = (size_t)(kMaxDigits + 1) * kMaxCols * 2;
+
+static int ctx_get(int device, DeviceCtx **out)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PQ_ERR_NO_DEVICE,
+                    std::string("no usable CUDA device (") +
+                        (e == cudaSuccess ? "device count 0" : cudaGetErrorString(e)) +
+                        "); libpqperm has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev)
+        return fail(PQ_ERR_BAD_ARG, "device index out of range");
+    if ((int)g_ctx.size() < ndev)
+        g_ctx.resize(ndev);
+    if (!g_ctx[device])
+        g_ctx[device].reset(new DeviceCtx());
+    DeviceCtx *c = g_ctx[device].get();
+    PQ_CUDA(cudaSetDevice(device));
+    if (!c->ready) {
+        c->device = device;
+        PQ_CUDA(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
+        PQ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        PQ_CUDA(cudaEventCreate(&c->ev0));
+        PQ_CUDA(cudaEventCreate(&c->ev1));
+        PQ_CUDA(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+        PQ_CUDA(cudaMalloc(&c->d_A2, kA2Doubles * sizeof(double)));
+        PQ_CUDA(cudaMalloc(&c->d_partials, (size_t)kMaxGrid * 4 * sizeof(double)));
+        PQ_CUDA(cudaMalloc(&c->d_out, 4 * sizeof(double)));
+        PQ_CUDA(cudaMalloc(&c->d_sched, (size_t)kMaxSegLenNary));
+        PQ_CUDA(cudaMalloc(&c->d_wtab, (size_t)kMaxSegLenNary * sizeof(double)));
+        PQ_CUDA(cudaMalloc(&c->d_binom, (size_t)kMaxDigits * 256 * sizeof(double)));
+        PQ_CUDA(cudaMallocHost(&c->h_pinned, (kA2Doubles + 8) * sizeof(double)));
+        c->ready = true;
+    }
+    *out = c;
+    return PQ_OK;
+}
+
+static void fill_params(const Plan &plan, DeviceCtx *c, WalkParams &P)
+{
+    std::memset(&P, 0, sizeof(P));
+    P.A2 = reinterpret_cast<const double2 *>(c->d_A2);
+    P.sched = c->d_sched;
+    P.wtab = c->d_wtab;
+    P.binom = c->d_binom;
+    P.partials = c->d_partials;
+    P.segsums = nullptr;
+    P.W = plan.W;
+    P.D = plan.D;
+    P.q = plan.q;
+    for (int d = 0; d < plan.D; d++) {
+        P.radix[d] = (uint8_t)(plan.mult[d] + 1);
+        P.mult[d] = (uint8_t)plan.mult[d];
+        P.binom_off[d] = (uint16_t)plan.binom_off[d];
+    }
+    for (int j = 0; j < plan.NCP; j++)
+        P.colmult[j] = (uint8_t)plan.colmult[j];
+}
+
+// Enqueue upload + walk + reduction of segments [seg_begin, seg_end) on c's
+// stream; the four-double partial lands in d_dst (device) on that stream.
+static int enqueue_walk(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64_t seg_end,
+                        double *d_dst, double *d_segsums, cudaStream_t stream)
+{
+    WalkParams P;
+    fill_params(plan, c, P);
+    P.seg_begin = seg_begin;
+    P.seg_end = seg_end;
+    P.segsums = d_segsums;
+
+    // the pinned staging buffer may still feed the previous (caller-stream) enqueue
+    if (c->up_pending) {
+        PQ_CUDA(cudaEventSynchronize(c->ev_up));
+        c->up_pending = false;
+    }
+    const size_t a2_bytes = plan.A2.size() * sizeof(double);
+    std::memcpy(c->h_pinned, plan.A2.data(), a2_bytes);
+    LaunchInfo info;
+    cudaError_t e;
+    PQ_CUDA(cudaMemcpyAsync(c->d_A2, c->h_pinned, a2_bytes, cudaMemcpyHostToDevice, stream));
+    if (!plan.binary && plan.W > 1) {
+        PQ_CUDA(cudaMemcpyAsync(c->d_sched, plan.sched.data(), (size_t)plan.W,
+                                cudaMemcpyHostToDevice, stream));
+        PQ_CUDA(cudaMemcpyAsync(c->d_wtab, plan.wtab.data(), (size_t)plan.W * sizeof(double),
+                                cudaMemcpyHostToDevice, stream));
+    }
+    if (!plan.binary && !plan.binom.empty())
+        PQ_CUDA(cudaMemcpyAsync(c->d_binom, plan.binom.data(),
+                                plan.binom.size() * sizeof(double), cudaMemcpyHostToDevice,
+                                stream));
+    PQ_CUDA(cudaEventRecord(c->ev_up, stream));
+    c->up_pending = true;
+    if (plan.kernel == 2) {
+        e = launch_binary(plan.NC, plan.B, plan.chains, P,
+                          reinterpret_cast<const double2 *>(c->d_A2),
+                          cudaMemcpyDeviceToDevice, c->num_sms, kMaxGrid, stream, &info);
+    } else {
+        e = launch_generic(plan.NCP, plan.binary && plan.unitcols, plan.binary && plan.unitcols,
+                           P, c->num_sms, kMaxGrid, stream, &info);
+    }
+    if (e != cudaSuccess)
+        return fail_cuda(e, plan.kernel == 2 ? "launch perm_walk_binary" : "launch perm_walk_generic");
+    e = launch_reduce_partials(c->d_partials, info.grid, d_dst, stream);
+    if (e != cudaSuccess)
+        return fail_cuda(e, "launch reduce_partials");
+    g_launches += 2;
+    return PQ_OK;
+}
+
+static PlanOptions plan_options(int num_sms)
+{
+    PlanOptions o;
+    o.kernel_choice = g_kernel_choice;
+    o.seg_len_hint = g_seg_len_hint;
+    o.num_sms = num_sms;
+    return o;
+}
+
+static void split_range(int64_t nseg, int part, int nparts, int64_t *b, int64_t *e)
+{
+    *b = (int64_t)(((__int128)nseg * part) / nparts);
+    *e = (int64_t)(((__int128)nseg * (part + 1)) / nparts);
+}
+
+} // namespace pqperm
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" int pq_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int pq_set_devices(const int *device_ids, int n)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (n < 1 || !device_ids)
+        return fail(PQ_ERR_BAD_ARG, "need at least one device id");
+    const int ndev = pq_device_count();
+    std::vector<int> ids(device_ids, device_ids + n);
+    for (int id : ids)
+        if (id < 0 || id >= ndev)
+            return fail(PQ_ERR_BAD_ARG, "device id out of range");
+    g_devices = ids;
+    return PQ_OK;
+}
+
+extern "C" int pq_set_kernel_choice(int choice)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_kernel_choice = choice;
+    return PQ_OK;
+}
+
+extern "C" int pq_set_seg_len_hint(int64_t seg_len)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_seg_len_hint = seg_len;
+    return PQ_OK;
+}
+
+extern "C" int64_t pq_launch_count(void) { return g_launches.load(); }
+
+extern "C" double pq_last_kernel_ms(int device)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (device < 0 || device >= (int)g_ctx.size() || !g_ctx[device])
+        return -1.0;
+    return g_ctx[device]->last_kernel_ms;
+}
+
+extern "C" int pq_perm_finish(const double partial[4], int sum_rows, double out[2])
+{
+    if (!partial || !out)
+        return fail(PQ_ERR_BAD_ARG, "null pointer");
+    // src/permanent.cpp:259: permanent /= 2^(sum_rows - 1); exact power-of-two scaling
+    out[0] = std::ldexp(partial[0] + partial[1], -(sum_rows - 1));
+    out[1] = std::ldexp(partial[2] + partial[3], -(sum_rows - 1));
+    return PQ_OK;
+}
+
+static void fill_info(const Plan &plan, pq_plan_info *info)
+{
+    std::memset(info, 0, sizeof(*info));
+    info->idx_max = plan.idx_max;
+    info->seg_len = plan.W;
+    info->nseg = plan.nseg;
+    info->active_rows = plan.D;
+    info->active_cols = plan.NC;
+    info->low_digits = plan.q;
+    info->kernel = plan.kernel;
+    info->cols_padded = plan.NCP;
+    info->sum_rows = plan.sum_rows;
+    info->trivial = plan.trivial;
+    info->flops_per_term = 2.0 * plan.NC + 6.0 * plan.M + 2.0;
+}
+
+extern "C" int pq_perm_plan(int R, int C, const int32_t *rows, const int32_t *cols,
+                            pq_plan_info *info)
+{
+    if (!info)
+        return fail(PQ_ERR_BAD_ARG, "null info");
+    Plan plan;
+    std::string err;
+    int num_sms = 148;
+    PlanOptions o;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        o = plan_options(num_sms);
+    }
+    const int rc = make_plan(nullptr, R, C, rows, cols, o, plan, err);
+    if (rc)
+        return fail(rc, err);
+    fill_info(plan, info);
+    return PQ_OK;
+}
+
+extern "C" int pq_perm_gray_of_offset(int R, const int32_t *rows, int64_t offset,
+                                      int32_t *gray)
+{
+    if (!gray || R <= 0 || !rows)
+        return fail(PQ_ERR_BAD_ARG, "bad arguments");
+    // multiplicity-only plan: one unit column per photon keeps the sum check happy
+    int64_t n = 0;
+    for (int i = 0; i < R; i++)
+        n += rows[i];
+    std::vector<int32_t> cols(1, (int32_t)n);
+    Plan plan;
+    std::string err;
+    PlanOptions o;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        o = plan_options(148);
+    }
+    const int rc = make_plan(nullptr, R, 1, rows, cols.data(), o, plan, err);
+    if (rc)
+        return fail(rc, err);
+    if (offset < 0 || offset >= plan.idx_max)
+        return fail(PQ_ERR_BAD_ARG, "offset outside [0, idx_max)");
+    plan_gray_of_offset(plan, offset, gray);
+    return PQ_OK;
+}
+
+// Shared body of pq_perm_c128 / partial / segment sums.
+static int perm_run(const double *A, int R, int C, const int32_t *rows, const int32_t *cols,
+                    double out[2])
+{
+    if (!out || (R > 0 && C > 0 && !A))
+        return fail(PQ_ERR_BAD_ARG, "null pointer");
+    std::lock_guard<std::mutex> lock(g_mu);
+    // validate / early-outs first: they need no device, exactly like the reference
+    Plan plan;
+    std::string err;
+    {
+        PlanOptions o = plan_options(148);
+        const int rc = make_plan(nullptr, R, C, rows, cols, o, plan, err);
+        if (rc)
+            return fail(rc, err);
+        if (plan.trivial) {
+            out[0] = plan.triv[0];
+            out[1] = plan.triv[1];
+            return PQ_OK;
+        }
+    }
+    const std::vector<int> devices = g_devices;
+    const int ndev = (int)devices.size();
+    std::vector<DeviceCtx *> ctx(ndev, nullptr);
+    for (int i = 0; i < ndev; i++) {
+        const int rc = ctx_get(devices[i], &ctx[i]);
+        if (rc)
+            return rc;
+    }
+    {
+        PlanOptions o = plan_options(ctx[0]->num_sms * ndev);
+        const int rc = make_plan(A, R, C, rows, cols, o, plan, err);
+        if (rc)
+            return fail(rc, err);
+    }
+    // small problems are not worth a second device
+    const int used = (ndev > 1 && plan.nseg >= (int64_t)ndev * 4096) ? ndev : 1;
+    for (int i = 0; i < used; i++) {
+        DeviceCtx *c = ctx[i];
+        PQ_CUDA(cudaSetDevice(c->device));
+        int64_t b, e;
+        split_range(plan.nseg, i, used, &b, &e);
+        PQ_CUDA(cudaEventRecord(c->ev0, c->stream));
+        const int rc = enqueue_walk(plan, c, b, e, c->d_out, nullptr, c->stream);
+        if (rc)
+            return rc;
+        PQ_CUDA(cudaEventRecord(c->ev1, c->stream));
+        PQ_CUDA(cudaMemcpyAsync(c->h_pinned + kA2Doubles, c->d_out, 4 * sizeof(double),
+                                cudaMemcpyDeviceToHost, c->stream));
+    }
+    double tot[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = 0; i < used; i++) {
+        DeviceCtx *c = ctx[i];
+        PQ_CUDA(cudaSetDevice(c->device));
+        PQ_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
+            c->last_kernel_ms = ms;
+        // fixed device order => reproducible; hi and lo parts are summed separately
+        for (int k = 0; k < 4; k++)
+            tot[k] += c->h_pinned[kA2Doubles + k];
+    }
+    return pq_perm_finish(tot, plan.sum_rows, out);
+}
+
+extern "C" int pq_perm_c128(const double *A, int R, int C, const int32_t *rows,
+                            const int32_t *cols, double out[2])
+{
+    return perm_run(A, R, C, rows, cols, out);
+}
+
+extern "C" int pq_perm_c64(const float *A, int R, int C, const int32_t *rows,
+                           const int32_t *cols, float out[2])
+{
+    if (!out || (R > 0 && C > 0 && !A))
+        return fail(PQ_ERR_BAD_ARG, "null pointer");
+    std::vector<double> Ad((size_t)(R > 0 ? R : 0) * (C > 0 ? C : 0) * 2);
+    for (size_t i = 0; i < Ad.size(); i++)
+        Ad[i] = (double)A[i];
+    double o[2];
+    const int rc = perm_run(Ad.data(), R, C, rows, cols, o);
+    if (rc)
+        return rc;
+    out[0] = (float)o[0];
+    out[1] = (float)o[1];
+    return PQ_OK;
+}
+
+extern "C" int pq_perm_partial_c128(const double *A, int R, int C, const int32_t *rows,
+                                    const int32_t *cols, int part, int nparts, int device,
+                                    void *stream, double *d_partial, int *status,
+                                    double trivial[2])
+{
+    if (!d_partial || nparts < 1 || part < 0 || part >= nparts)
+        return fail(PQ_ERR_BAD_ARG, "bad partition arguments");
+    std::lock_guard<std::mutex> lock(g_mu);
+    Plan plan;
+    std::string err;
+    {
+        PlanOptions o = plan_options(148);
+        const int rc = make_plan(nullptr, R, C, rows, cols, o, plan, err);
+        if (rc)
+            return fail(rc, err);
+        if (plan.trivial) {
+            if (status)
+                *status = 1;
+            if (trivial) {
+                trivial[0] = plan.triv[0];
+                trivial[1] = plan.triv[1];
+            }
+            return PQ_OK;
+        }
+    }
+    DeviceCtx *c = nullptr;
+    int rc = ctx_get(device, &c);
+    if (rc)
+        return rc;
+    {
+        // plan for the whole job so that every rank cuts the term space identically
+        PlanOptions o = plan_options(c->num_sms * nparts);
+        rc = make_plan(A, R, C, rows, cols, o, plan, err);
+        if (rc)
+            return fail(rc, err);
+    }
+    int64_t b, e;
+    split_range(plan.nseg, part, nparts, &b, &e);
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    PQ_CUDA(cudaEventRecord(c->ev0, s));
+    if (b < e) {
+        rc = enqueue_walk(plan, c, b, e, d_partial, nullptr, s);
+        if (rc)
+            return rc;
+    } else {
+        PQ_CUDA(cudaMemsetAsync(d_partial, 0, 4 * sizeof(double), s));
+    }
+    PQ_CUDA(cudaEventRecord(c->ev1, s));
+    if (!stream) {
+        PQ_CUDA(cudaStreamSynchronize(s));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
+            c->last_kernel_ms = ms;
+    }
+    if (status)
+        *status = 0;
+    return PQ_OK;
+}
+
+extern "C" int pq_perm_segment_sums_c128(const double *A, int R, int C, const int32_t *rows,
+                                         const int32_t *cols, int64_t seg_begin,
+                                         int64_t nseg, double *out)
+{
+    if (!out || nseg < 1 || seg_begin < 0)
+        return fail(PQ_ERR_BAD_ARG, "bad segment range");
+    std::lock_guard<std::mutex> lock(g_mu);
+    DeviceCtx *c = nullptr;
+    int rc = ctx_get(g_devices[0], &c);
+    if (rc)
+        return rc;
+    Plan plan;
+    std::string err;
+    PlanOptions o = plan_options(c->num_sms);
+    rc = make_plan(A, R, C, rows, cols, o, plan, err);
+    if (rc)
+        return fail(rc, err);
+    if (plan.trivial)
+        return fail(PQ_ERR_BAD_ARG, "trivial problem has no segments");
+    if (seg_begin + nseg > plan.nseg)
+        return fail(PQ_ERR_BAD_ARG, "segment range outside the plan");
+    double *d_seg = nullptr;
+    PQ_CUDA(cudaMalloc(&d_seg, (size_t)nseg * 2 * sizeof(double)));
+    rc = enqueue_walk(plan, c, seg_begin, seg_begin + nseg, c->d_out, d_seg, c->stream);
+    if (rc == PQ_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d_seg, (size_t)nseg * 2 * sizeof(double),
+                                        cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess)
+            rc = fail_cuda(e, "segment sums copy");
+    }
+    cudaFree(d_seg);
+    return rc;
+}
+
+extern "C" double pq_fp64_peak_tflops(int device, int iters)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    DeviceCtx *c = nullptr;
+    if (ctx_get(device, &c))
+        return -1.0;
+    if (iters < 1)
+        iters = 1 << 16;
+    double best = -1.0;
+    for (int rep = 0; rep < 4; rep++) { // first pass is the warm-up
+        double flops = 0.0;
+        if (cudaEventRecord(c->ev0, c->stream) != cudaSuccess)
+            return -1.0;
+        if (launch_dfma_probe(c->num_sms, iters, c->d_out, c->stream, &flops) != cudaSuccess)
+            return -1.0;
+        g_launches += 1;
+        cudaEventRecord(c->ev1, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess)
+            return -1.0;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        if (rep > 0 && ms > 0.f)
+            best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    return best;
+}
+
+// ---- Laplace entries (kernels in pqperm_kernels_laplace.cu) -----------------
+extern "C" int pq_perm_laplace_c128(const double *A, int R, int C, const int32_t *rows,
+                                    const int32_t *cols, double *out, int *out_len)
+{
+    if (!out || !out_len || (R > 0 && C > 0 && !A))
+        return fail(PQ_ERR_BAD_ARG, "null pointer");
+    std::lock_guard<std::mutex> lock(g_mu);
+    std::string err;
+    const int rc = laplace_run(g_devices[0], A, R, C, rows, cols, out, out_len, err);
+    if (rc)
+        return fail(rc, err);
+    return PQ_OK;
+}
+
+extern "C" int pq_perm_laplace_c64(const float *A, int R, int C, const int32_t *rows,
+                                   const int32_t *cols, float *out, int *out_len)
+{
+    if (!out || !out_len || (R > 0 && C > 0 && !A))
+        return fail(PQ_ERR_BAD_ARG, "null pointer");
+    std::vector<double> Ad((size_t)(R > 0 ? R : 0) * (C > 0 ? C : 0) * 2);
+    for (size_t i = 0; i < Ad.size(); i++)
+        Ad[i] = (double)A[i];
+    std::vector<double> o(2 * (size_t)(C > 0 ? C : 1));
+    const int rc = pq_perm_laplace_c128(Ad.data(), R, C, rows, cols, o.data(), out_len);
+    if (rc)
+        return rc;
+    for (int i = 0; i < 2 * *out_len; i++)
+        out[i] = (float)o[i];
+    return PQ_OK;
+}

@@ -1,0 +1,105 @@
+// pqperm_device.cuh -- parameter blocks and device helpers shared by the
+// permanent kernels (sm_100a).  See DESIGN.md for the data layout.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pqperm_limits.h"
+
+namespace pqperm {
+
+// Parameter block of the single-permanent walks.  Passed by value as a
+// __grid_constant__ so that the small per-digit tables (and, for the binary
+// kernel, the rows of the lowest Gray digits) sit in the constant bank and
+// can be used as immediate-offset operands of FP64 instructions.
+struct WalkParams {
+    const double2 *A2;     // (D+1) x NC: row 0 = pinned row a_0, rows 1..D = 2*a_d
+    const uint8_t *sched;  // [W] digit that moves on the step INTO local index m (n-ary only)
+    const double *wtab;    // [W] (-1)^m * prod_low C(r_i, c_i(m))           (n-ary only)
+    const double *binom;   // flattened C(r_d, g) tables, binom_off[d] + g
+    double *partials;      // [gridDim.x][4] re_hi, re_lo, im_hi, im_lo
+    double *segsums;       // optional [seg_end - seg_begin][2] per-segment sums
+    long long seg_begin;   // segments [seg_begin, seg_end) belong to this launch
+    long long seg_end;
+    long long W;           // terms per segment = prod_{d<q} radix[d]
+    int D;                 // Gray digits
+    int q;                 // digits 0..q-1 are walked inside the segment
+    uint8_t radix[kMaxDigits];    // r_d + 1
+    uint8_t mult[kMaxDigits];     // r_d
+    uint8_t colmult[kMaxCols];    // c_j (1 for padding columns)
+    uint16_t binom_off[kMaxDigits];
+};
+
+// ---- double-double accumulation -------------------------------------------
+
+struct dd {
+    double hi, lo;
+};
+
+// a += b with the rounding error of the high part collected in lo (TwoSum).
+__device__ __forceinline__ void dd_add(dd &a, double b)
+{
+    const double s = a.hi + b;
+    const double bb = s - a.hi;
+    const double e = (a.hi - (s - bb)) + (b - bb);
+    a.hi = s;
+    a.lo += e;
+}
+
+__device__ __forceinline__ void dd_add(dd &a, const dd &b)
+{
+    dd_add(a, b.hi);
+    a.lo += b.lo;
+}
+
+__device__ __forceinline__ dd dd_shfl_down(const dd &a, int delta)
+{
+    dd r;
+    r.hi = __shfl_down_sync(0xffffffffu, a.hi, delta);
+    r.lo = __shfl_down_sync(0xffffffffu, a.lo, delta);
+    return r;
+}
+
+// Sum (re, im) double-double pairs over the block; thread 0 writes 4 doubles.
+// Fixed tree => bit-reproducible for a fixed launch geometry.
+template <int NT>
+__device__ __forceinline__ void block_reduce_store(dd re, dd im, double *out4)
+{
+    __shared__ double red[(NT / 32) * 4];
+#pragma unroll
+    for (int delta = 16; delta > 0; delta >>= 1) {
+        dd_add(re, dd_shfl_down(re, delta));
+        dd_add(im, dd_shfl_down(im, delta));
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        red[warp * 4 + 0] = re.hi;
+        red[warp * 4 + 1] = re.lo;
+        red[warp * 4 + 2] = im.hi;
+        red[warp * 4 + 3] = im.lo;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        dd r{red[0], red[1]}, i{red[2], red[3]};
+        for (int w = 1; w < NT / 32; w++) {
+            dd_add(r, dd{red[w * 4 + 0], red[w * 4 + 1]});
+            dd_add(i, dd{red[w * 4 + 2], red[w * 4 + 3]});
+        }
+        out4[0] = r.hi;
+        out4[1] = r.lo;
+        out4[2] = i.hi;
+        out4[3] = i.lo;
+    }
+}
+
+// complex multiply-in-place: (pr, pi) *= (sr, si); 2 DMUL + 2 DFMA
+__device__ __forceinline__ void cmul(double &pr, double &pi, double sr, double si)
+{
+    const double nr = __fma_rn(pr, sr, -(pi * si));
+    const double ni = __fma_rn(pr, si, pi * sr);
+    pr = nr;
+    pi = ni;
+}
+
+} // namespace pqperm
