@@ -40,7 +40,8 @@ def _units():
         ("api", "pqperm_api.cu", []),
         ("plan", "pqperm_plan.cpp", []),
         ("generic", "pqperm_kernels_generic.cu", []),
-        ("laplace", "pqperm_kernels_laplace.cu", []),
+        ("laplace_unit", "pqperm_kernels_laplace.cu", ["-DPQ_LAP_UNIT=1"]),
+        ("laplace_general", "pqperm_kernels_laplace.cu", ["-DPQ_LAP_UNIT=0"]),
     ]
     for part, lo, hi in BINARY_PARTS:
         units.append((

@@ -43,10 +43,6 @@ cudaError_t launch_binary(int nc, int B, int chains, const WalkParams &P,
     return launch_binary_part_3(nc, B, chains, P, A2_src, kind, num_sms, max_grid, stream, info);
 }
 
-// Laplace kernels (pqperm_kernels_laplace.cu)
-int laplace_run(int dev_slot, const double *A, int R, int C, const int32_t *rows,
-                const int32_t *cols, double *out, int *out_len, std::string &err);
-
 } // namespace pqperm
 
 using namespace pqperm;
@@ -98,12 +94,18 @@ struct DeviceCtx {
     double *d_A2 = nullptr;        // (kMaxDigits+1) x kMaxCols double2
     double *d_partials = nullptr;  // kMaxGrid x 4
     double *d_out = nullptr;       // 4 doubles
+    unsigned long long *d_counter = nullptr;  // segment dispenser of the walk kernels
     uint8_t *d_sched = nullptr;    // kMaxSegLenNary
     double *d_wtab = nullptr;      // kMaxSegLenNary
     double *d_binom = nullptr;     // kMaxDigits * 256
     double *h_pinned = nullptr;    // staging: A2 + out
     double last_kernel_ms = -1.0;
     bool ready = false;
+    // growable buffers of the batched Laplace path
+    void *d_lap[4] = {nullptr, nullptr, nullptr, nullptr};   // prob, A2, partials, out
+    size_t d_lap_cap[4] = {0, 0, 0, 0};
+    void *h_lap[3] = {nullptr, nullptr, nullptr};            // prob, A2, out (pinned)
+    size_t h_lap_cap[3] = {0, 0, 0};
 };
 
 static std::mutex g_mu;                 // one caller at a time (GIL-held callers anyway)
@@ -144,6 +146,7 @@ static int ctx_get(int device, DeviceCtx **out)
         PQ_CUDA(cudaMalloc(&c->d_A2, kA2Doubles * sizeof(double)));
         PQ_CUDA(cudaMalloc(&c->d_partials, (size_t)kMaxGrid * 4 * sizeof(double)));
         PQ_CUDA(cudaMalloc(&c->d_out, 4 * sizeof(double)));
+        PQ_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned long long)));
         PQ_CUDA(cudaMalloc(&c->d_sched, (size_t)kMaxSegLenNary));
         PQ_CUDA(cudaMalloc(&c->d_wtab, (size_t)kMaxSegLenNary * sizeof(double)));
         PQ_CUDA(cudaMalloc(&c->d_binom, (size_t)kMaxDigits * 256 * sizeof(double)));
@@ -163,6 +166,7 @@ static void fill_params(const Plan &plan, DeviceCtx *c, WalkParams &P)
     P.binom = c->d_binom;
     P.partials = c->d_partials;
     P.segsums = nullptr;
+    P.counter = c->d_counter;
     P.W = plan.W;
     P.D = plan.D;
     P.q = plan.q;
@@ -196,16 +200,18 @@ static int enqueue_walk(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64
     LaunchInfo info;
     cudaError_t e;
     PQ_CUDA(cudaMemcpyAsync(c->d_A2, c->h_pinned, a2_bytes, cudaMemcpyHostToDevice, stream));
-    if (!plan.binary && plan.W > 1) {
+    const bool fast = plan.binary && plan.unitcols; // tables are needed otherwise
+    if (!fast && plan.W > 1) {
         PQ_CUDA(cudaMemcpyAsync(c->d_sched, plan.sched.data(), (size_t)plan.W,
                                 cudaMemcpyHostToDevice, stream));
         PQ_CUDA(cudaMemcpyAsync(c->d_wtab, plan.wtab.data(), (size_t)plan.W * sizeof(double),
                                 cudaMemcpyHostToDevice, stream));
     }
-    if (!plan.binary && !plan.binom.empty())
+    if (!fast && !plan.binom.empty())
         PQ_CUDA(cudaMemcpyAsync(c->d_binom, plan.binom.data(),
                                 plan.binom.size() * sizeof(double), cudaMemcpyHostToDevice,
                                 stream));
+    PQ_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), stream));
     PQ_CUDA(cudaEventRecord(c->ev_up, stream));
     c->up_pending = true;
     if (plan.kernel == 2) {
@@ -213,8 +219,7 @@ static int enqueue_walk(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64
                           reinterpret_cast<const double2 *>(c->d_A2),
                           cudaMemcpyDeviceToDevice, c->num_sms, kMaxGrid, stream, &info);
     } else {
-        e = launch_generic(plan.NCP, plan.binary && plan.unitcols, plan.binary && plan.unitcols,
-                           P, c->num_sms, kMaxGrid, stream, &info);
+        e = launch_generic(plan.NCP, fast, fast, P, c->num_sms, kMaxGrid, stream, &info);
     }
     if (e != cudaSuccess)
         return fail_cuda(e, plan.kernel == 2 ? "launch perm_walk_binary" : "launch perm_walk_generic");
@@ -575,17 +580,253 @@ extern "C" double pq_fp64_peak_tflops(int device, int iters)
     return best;
 }
 
-// ---- Laplace entries (kernels in pqperm_kernels_laplace.cu) -----------------
+// ---------------------------------------------------------------------------
+// permanent_laplace: single call and batch (kernels: pqperm_laplace.cuh)
+// ---------------------------------------------------------------------------
+namespace pqperm {
+
+static int grow_dev(DeviceCtx *c, int slot, size_t bytes)
+{
+    if (c->d_lap_cap[slot] >= bytes)
+        return PQ_OK;
+    if (c->d_lap[slot])
+        cudaFree(c->d_lap[slot]);
+    c->d_lap[slot] = nullptr;
+    c->d_lap_cap[slot] = 0;
+    const size_t cap = bytes + bytes / 2 + 4096;
+    PQ_CUDA(cudaMalloc(&c->d_lap[slot], cap));
+    c->d_lap_cap[slot] = cap;
+    return PQ_OK;
+}
+
+static int grow_host(DeviceCtx *c, int slot, size_t bytes)
+{
+    if (c->h_lap_cap[slot] >= bytes)
+        return PQ_OK;
+    if (c->h_lap[slot])
+        cudaFreeHost(c->h_lap[slot]);
+    c->h_lap[slot] = nullptr;
+    c->h_lap_cap[slot] = 0;
+    const size_t cap = bytes + bytes / 2 + 4096;
+    PQ_CUDA(cudaMallocHost(&c->h_lap[slot], cap));
+    c->h_lap_cap[slot] = cap;
+    return PQ_OK;
+}
+
+struct LapItem {
+    int index;   // problem index in the caller's batch
+    Plan plan;
+};
+
+// Run one group of problems that share a kernel variant (same S, NCL, unit
+// flag); results are scattered into the caller's `out`.
+static int laplace_group(DeviceCtx *c, std::vector<LapItem> &items, int S, int NCL,
+                         bool unitcols, const int32_t *C, const int32_t *cols,
+                         const int64_t *c_off, double *out, const int64_t *o_off)
+{
+    const int n = (int)items.size();
+    const int NCP = S * NCL, ncp1 = NCP + 1;
+    // CTAs per problem: enough to cover its segments, bounded so that the
+    // whole group is a few waves of the machine
+    const int groups_per_block = kLapThreads / S;
+    const long long wave = (long long)c->num_sms * 8;
+    long long budget = std::max<long long>(1, (4 * wave) / n);
+    size_t a2_elems = 0;
+    int total_blocks = 0, max_D = 0;
+    int rc = grow_host(c, 0, sizeof(LapProblem) * (size_t)n);
+    if (rc)
+        return rc;
+    LapProblem *hp = reinterpret_cast<LapProblem *>(c->h_lap[0]);
+    for (int i = 0; i < n; i++) {
+        const Plan &pl = items[i].plan;
+        LapProblem &q = hp[i];
+        std::memset(&q, 0, sizeof(q));
+        q.a_off = (long long)a2_elems;
+        q.nseg = pl.nseg;
+        long long nb = (pl.nseg + groups_per_block - 1) / groups_per_block;
+        nb = std::max<long long>(1, std::min(nb, budget));
+        q.first_block = total_blocks;
+        q.nblocks = (int)nb;
+        q.D = pl.D;
+        q.q = pl.q;
+        q.W = (int)pl.W;
+        q.exp2 = pl.sum_rows - 1;
+        for (int d = 0; d < pl.D; d++)
+            q.mult[d] = (uint8_t)pl.mult[d];
+        for (int j = 0; j < NCP; j++)
+            q.colmult[j] = (uint8_t)pl.colmult[j];
+        total_blocks += (int)nb;
+        a2_elems += (size_t)(pl.D + 1) * NCP;
+        max_D = std::max(max_D, pl.D);
+    }
+    rc = grow_host(c, 1, a2_elems * sizeof(double2));
+    if (rc)
+        return rc;
+    double *ha = reinterpret_cast<double *>(c->h_lap[1]);
+    for (int i = 0; i < n; i++)
+        std::memcpy(ha + 2 * hp[i].a_off, items[i].plan.A2.data(),
+                    items[i].plan.A2.size() * sizeof(double));
+    const size_t out_bytes = (size_t)n * ncp1 * sizeof(double2);
+    if ((rc = grow_host(c, 2, out_bytes)) || (rc = grow_dev(c, 0, sizeof(LapProblem) * (size_t)n)) ||
+        (rc = grow_dev(c, 1, a2_elems * sizeof(double2))) ||
+        (rc = grow_dev(c, 2, (size_t)total_blocks * ncp1 * sizeof(double2))) ||
+        (rc = grow_dev(c, 3, out_bytes)))
+        return rc;
+    cudaStream_t st = c->stream;
+    PQ_CUDA(cudaMemcpyAsync(c->d_lap[0], hp, sizeof(LapProblem) * (size_t)n,
+                            cudaMemcpyHostToDevice, st));
+    PQ_CUDA(cudaMemcpyAsync(c->d_lap[1], ha, a2_elems * sizeof(double2),
+                            cudaMemcpyHostToDevice, st));
+    LapParams P;
+    P.prob = reinterpret_cast<const LapProblem *>(c->d_lap[0]);
+    P.A2 = reinterpret_cast<const double2 *>(c->d_lap[1]);
+    P.partials = reinterpret_cast<double2 *>(c->d_lap[2]);
+    P.out = reinterpret_cast<double2 *>(c->d_lap[3]);
+    P.nprob = n;
+    const size_t smem = (size_t)(max_D + 1) * NCP * sizeof(double2);
+    PQ_CUDA(cudaEventRecord(c->ev0, st));
+    cudaError_t e = launch_laplace(S, NCL, unitcols, P, total_blocks, smem, st);
+    if (e != cudaSuccess)
+        return fail_cuda(e, "launch laplace_walk_kernel");
+    e = launch_laplace_reduce(P, ncp1, st);
+    if (e != cudaSuccess)
+        return fail_cuda(e, "launch laplace_reduce_kernel");
+    g_launches += 2;
+    PQ_CUDA(cudaEventRecord(c->ev1, st));
+    PQ_CUDA(cudaMemcpyAsync(c->h_lap[2], c->d_lap[3], out_bytes, cudaMemcpyDeviceToHost, st));
+    PQ_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
+        c->last_kernel_ms = (c->last_kernel_ms < 0 ? 0.0 : c->last_kernel_ms) + ms;
+    // scatter: compact column k -> original column src_col[k]; columns with
+    // multiplicity 0 receive the full product (reference quirk)
+    const double *ho = reinterpret_cast<const double *>(c->h_lap[2]);
+    for (int i = 0; i < n; i++) {
+        const Plan &pl = items[i].plan;
+        const int b = items[i].index;
+        const double *res = ho + (size_t)i * ncp1 * 2;
+        double *dst = out + 2 * o_off[b];
+        const int32_t *cm = cols + c_off[b];
+        int k = 0;
+        for (int j = 0; j < C[b]; j++) {
+            if (cm[j] > 0) {
+                dst[2 * j] = res[2 * k];
+                dst[2 * j + 1] = res[2 * k + 1];
+                k++;
+            } else {
+                dst[2 * j] = res[2 * NCP];
+                dst[2 * j + 1] = res[2 * NCP + 1];
+            }
+        }
+        (void)pl;
+    }
+    return PQ_OK;
+}
+
+static int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off,
+                                const int32_t *R, const int32_t *C, const int32_t *rows,
+                                const int64_t *r_off, const int32_t *cols,
+                                const int64_t *c_off, double *out, const int64_t *o_off,
+                                int32_t *out_len)
+{
+    // plan every problem first: validation and early-outs need no device
+    std::vector<LapItem> items;
+    items.reserve(nprob);
+    std::string err;
+    PlanOptions o = plan_options(148);
+    o.laplace = true;
+    o.kernel_choice = 1;
+    o.batch = std::max(1, nprob);
+    int num_sms = 148;
+    DeviceCtx *c = nullptr;
+    for (int b = 0; b < nprob; b++) {
+        if (R[b] < 0 || C[b] < 0)
+            return fail(PQ_ERR_BAD_ARG, "negative shape in batch");
+        LapItem it;
+        it.index = b;
+        // cheap structural pass first (no matrix) to catch the early-out
+        int rc = make_plan(nullptr, R[b], C[b], rows + r_off[b], cols + c_off[b], o, it.plan, err);
+        if (rc)
+            return fail(rc, err);
+        if (it.plan.trivial) {
+            out[2 * o_off[b]] = 1.0; // src/permanent_laplace.cpp:52-57
+            out[2 * o_off[b] + 1] = 0.0;
+            out_len[b] = 1;
+            continue;
+        }
+        if (!c) {
+            rc = ctx_get(g_devices[0], &c);
+            if (rc)
+                return rc;
+            num_sms = c->num_sms;
+            o.num_sms = num_sms;
+        }
+        rc = make_plan(A + 2 * a_off[b], R[b], C[b], rows + r_off[b], cols + c_off[b], o,
+                       it.plan, err);
+        if (rc)
+            return fail(rc, err);
+        out_len[b] = C[b];
+        items.push_back(std::move(it));
+    }
+    if (items.empty())
+        return PQ_OK;
+    c->last_kernel_ms = -1.0;
+    // group by kernel variant
+    std::vector<char> done(items.size(), 0);
+    for (size_t i = 0; i < items.size(); i++) {
+        if (done[i])
+            continue;
+        const LapVariant v = laplace_variant(items[i].plan.NC);
+        const bool unit = items[i].plan.unitcols;
+        std::vector<LapItem> group;
+        for (size_t k = i; k < items.size(); k++) {
+            if (done[k])
+                continue;
+            const LapVariant vk = laplace_variant(items[k].plan.NC);
+            if (vk.S == v.S && vk.NCL == v.NCL && items[k].plan.unitcols == unit) {
+                group.push_back(std::move(items[k]));
+                done[k] = 1;
+            }
+        }
+        const int rc = laplace_group(c, group, v.S, v.NCL, unit, C, cols, c_off, out, o_off);
+        if (rc)
+            return rc;
+    }
+    return PQ_OK;
+}
+
+} // namespace pqperm
+
+extern "C" int pq_perm_laplace_batch_c128(int nprob, const double *A, const int64_t *a_off,
+                                          const int32_t *R, const int32_t *C,
+                                          const int32_t *rows, const int64_t *r_off,
+                                          const int32_t *cols, const int64_t *c_off,
+                                          double *out, const int64_t *o_off,
+                                          int32_t *out_len)
+{
+    if (nprob < 0 || (nprob > 0 && (!a_off || !R || !C || !r_off || !c_off || !out ||
+                                    !o_off || !out_len)))
+        return fail(PQ_ERR_BAD_ARG, "null pointer in batch call");
+    if (nprob == 0)
+        return PQ_OK;
+    std::lock_guard<std::mutex> lock(g_mu);
+    return laplace_batch_locked(nprob, A, a_off, R, C, rows, r_off, cols, c_off, out, o_off,
+                                out_len);
+}
+
 extern "C" int pq_perm_laplace_c128(const double *A, int R, int C, const int32_t *rows,
                                     const int32_t *cols, double *out, int *out_len)
 {
     if (!out || !out_len || (R > 0 && C > 0 && !A))
         return fail(PQ_ERR_BAD_ARG, "null pointer");
-    std::lock_guard<std::mutex> lock(g_mu);
-    std::string err;
-    const int rc = laplace_run(g_devices[0], A, R, C, rows, cols, out, out_len, err);
+    const int64_t zero = 0;
+    const int32_t r32 = R, c32 = C;
+    int32_t len = 0;
+    const int rc = pq_perm_laplace_batch_c128(1, A, &zero, &r32, &c32, rows, &zero, cols, &zero,
+                                              out, &zero, &len);
     if (rc)
-        return fail(rc, err);
+        return rc;
+    *out_len = len;
     return PQ_OK;
 }
 

@@ -20,6 +20,7 @@ struct WalkParams {
     const double *binom;   // flattened C(r_d, g) tables, binom_off[d] + g
     double *partials;      // [gridDim.x][4] re_hi, re_lo, im_hi, im_lo
     double *segsums;       // optional [seg_end - seg_begin][2] per-segment sums
+    unsigned long long *counter;  // next undistributed segment (relative), zeroed per launch
     long long seg_begin;   // segments [seg_begin, seg_end) belong to this launch
     long long seg_end;
     long long W;           // terms per segment = prod_{d<q} radix[d]
@@ -29,6 +30,29 @@ struct WalkParams {
     uint8_t mult[kMaxDigits];     // r_d
     uint8_t colmult[kMaxCols];    // c_j (1 for padding columns)
     uint16_t binom_off[kMaxDigits];
+};
+
+// ---- batched Laplace walk (pqperm_laplace.cuh) ------------------------------
+
+struct LapProblem {
+    long long a_off;     // first double2 of this problem's (D+1) x NCP matrix in the pack
+    long long nseg;      // Gray segments
+    int first_block;     // CTAs [first_block, first_block + nblocks) work on this problem
+    int nblocks;
+    int D;               // Gray digits
+    int q;               // low digits walked inside a segment
+    int W;               // terms per segment
+    int exp2;            // results are scaled by 2^-exp2 (= sum_rows - 1)
+    uint8_t mult[kMaxDigits];    // r_d
+    uint8_t colmult[kMaxCols];   // c_j (1 for padding columns)
+};
+
+struct LapParams {
+    const LapProblem *prob;
+    const double2 *A2;   // packed matrices
+    double2 *partials;   // [total CTAs][NCP + 1]
+    double2 *out;        // [nprob][NCP + 1]: per compact column, then the full product
+    int nprob;
 };
 
 // ---- double-double accumulation -------------------------------------------

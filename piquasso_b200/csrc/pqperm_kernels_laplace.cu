@@ -1,18 +1,76 @@
-// placeholder until the Laplace walk lands
-#include <string>
-#include "../../include/pqperm.h"
+// pqperm_kernels_laplace.cu -- instantiations of the batched Laplace walk.
+// Compiled twice: -DPQ_LAP_UNIT=1 (all column multiplicities 1, what the
+// sampler issues for single-photon inputs) and -DPQ_LAP_UNIT=0 (general).
+#include <map>
+#include <mutex>
+
+#include "pqperm_launch.h"
+#include "pqperm_laplace.cuh"
+
+#ifndef PQ_LAP_UNIT
+#error "PQ_LAP_UNIT must be defined"
+#endif
+
 namespace pqperm {
-int laplace_run(int, const double *, int, int, const int *, const int *, double *, int *,
-                std::string &err)
+
+template <int NCL, int S>
+static cudaError_t launch_one(const LapParams &P, int total_blocks, size_t smem,
+                              cudaStream_t stream)
 {
-    err = "permanent_laplace kernels not built";
-    return PQ_ERR_CUDA;
+    auto kernel = laplace_walk_kernel<NCL, S, PQ_LAP_UNIT != 0>;
+    if (smem > 48 * 1024) {
+        static std::mutex mu;
+        static std::map<int, size_t> raised; // device -> largest limit set
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lock(mu);
+        if (raised[dev] < smem) {
+            cudaError_t e = cudaFuncSetAttribute(
+                kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess)
+                return e;
+            raised[dev] = smem;
+        }
+    }
+    kernel<<<total_blocks, kLapThreads, smem, stream>>>(P);
+    return cudaGetLastError();
 }
+
+#if PQ_LAP_UNIT
+cudaError_t launch_laplace_unit(
+#else
+cudaError_t launch_laplace_general(
+#endif
+    int S, int NCL, const LapParams &P, int total_blocks, size_t smem, cudaStream_t stream)
+{
+#define PQ_CASE(SS, NN)                                                                 \
+    if (S == SS && NCL == NN)                                                           \
+        return launch_one<NN, SS>(P, total_blocks, smem, stream);
+    PQ_CASE(1, 1) PQ_CASE(1, 2) PQ_CASE(1, 3) PQ_CASE(1, 4) PQ_CASE(1, 5) PQ_CASE(1, 6)
+    PQ_CASE(1, 7) PQ_CASE(1, 8)
+    PQ_CASE(2, 5) PQ_CASE(2, 6) PQ_CASE(2, 7) PQ_CASE(2, 8) PQ_CASE(2, 9) PQ_CASE(2, 10) PQ_CASE(2, 11) PQ_CASE(2, 12)
+    PQ_CASE(2, 13)
+    PQ_CASE(4, 7) PQ_CASE(4, 8) PQ_CASE(4, 9) PQ_CASE(4, 10) PQ_CASE(4, 11) PQ_CASE(4, 12)
+    PQ_CASE(4, 13) PQ_CASE(4, 14) PQ_CASE(4, 15) PQ_CASE(4, 16)
+#undef PQ_CASE
+    return cudaErrorInvalidValue;
+}
+
+#if PQ_LAP_UNIT
+cudaError_t launch_laplace_general(int, int, const LapParams &, int, size_t, cudaStream_t);
+
+cudaError_t launch_laplace(int S, int NCL, bool unitcols, const LapParams &P,
+                           int total_blocks, size_t smem, cudaStream_t stream)
+{
+    return unitcols ? launch_laplace_unit(S, NCL, P, total_blocks, smem, stream)
+                    : launch_laplace_general(S, NCL, P, total_blocks, smem, stream);
+}
+
+cudaError_t launch_laplace_reduce(const LapParams &P, int ncp1, cudaStream_t stream)
+{
+    laplace_reduce_kernel<<<(P.nprob + 3) / 4, 128, 0, stream>>>(P, ncp1);
+    return cudaGetLastError();
+}
+#endif
+
 } // namespace pqperm
-extern "C" int pq_perm_laplace_batch_c128(int, const double *, const int64_t *, const int32_t *,
-                                          const int32_t *, const int32_t *, const int64_t *,
-                                          const int32_t *, const int64_t *, double *,
-                                          const int64_t *, int32_t *)
-{
-    return PQ_ERR_CUDA;
-}

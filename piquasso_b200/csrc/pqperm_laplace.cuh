@@ -1,0 +1,300 @@
+// pqperm_laplace.cuh -- batched Laplace-expansion walk (sm_100a).
+//
+// Replaces the hot loop of permanent_laplace_cpp, src/permanent_laplace.cpp:
+// 191-223 of the reference: the same Gray-code walk as the permanent, but every
+// term contributes to C sums, sum l getting the product with ONE factor of
+// column l removed (Lemma 1 of arXiv:2005.04214):
+//   out_l * 2^(N-1) = sum_offset (-1)^{sum g} prod_d C(r_d,g_d)
+//                       * s_l^{c_l-1} prod_{k != l} s_k^{c_k}
+// The reference recomputes each of the C products from scratch (O(C*M) per
+// term); here one suffix pass + one prefix pass give all of them in 3 complex
+// multiplies per column.
+//
+// Batch layout: one launch walks many independent problems (the sampler's
+// (shot, photon) problems).  A CTA works on one problem; S adjacent lanes
+// ("group") share one Gray segment and split the columns (lane h owns columns
+// h, h+S, ...), so that row sums, suffix products and accumulators of up to 64
+// columns stay in registers.
+#pragma once
+
+#include "pqperm_device.cuh"
+
+namespace pqperm {
+
+__device__ __forceinline__ double small_binom(int n, int k)
+{
+    if (k > n - k)
+        k = n - k;
+    double r = 1.0;
+    for (int i = 1; i <= k; i++)
+        r = r * (double)(n - k + i) / (double)i;
+    return r;
+}
+
+template <int NCL, int S, bool UNITCOLS>
+__global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapParams P)
+{
+    constexpr int NCP = NCL * S;
+    constexpr int NT = kLapThreads;
+    extern __shared__ double2 smA[];              // (D+1) x NCP
+    __shared__ double s_wtab[kLapMaxSegLen];
+    __shared__ uint8_t s_sched[kLapMaxSegLen];
+    __shared__ int s_prob;
+
+    // ---- which problem does this CTA belong to (binary search over first_block)
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = P.nprob - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (P.prob[mid].first_block <= (int)blockIdx.x)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        s_prob = lo;
+    }
+    __syncthreads();
+    const LapProblem &Q = P.prob[s_prob];
+    const int D = Q.D, q = Q.q, W = Q.W;
+    {
+        const double2 *src = P.A2 + Q.a_off;
+        const int nelem = (D + 1) * NCP;
+        for (int i = threadIdx.x; i < nelem; i += NT)
+            smA[i] = src[i];
+        // step table of the low counter: digit moved on the step into m, and
+        // (-1)^m prod_{d<q} C(r_d, c_d(m))   (cf. pqperm_plan.cpp)
+        for (int m = threadIdx.x; m < W; m += NT) {
+            int rest = m, p = -1;
+            double w = (m & 1) ? -1.0 : 1.0;
+            for (int d = 0; d < q; d++) {
+                const int L = Q.mult[d] + 1;
+                const int c = rest % L;
+                rest /= L;
+                if (p < 0 && c != 0)
+                    p = d;
+                if (c != 0 && c != Q.mult[d])
+                    w *= small_binom(Q.mult[d], c);
+            }
+            s_sched[m] = (uint8_t)(p < 0 ? 0 : p);
+            s_wtab[m] = w;
+        }
+    }
+    __syncthreads();
+
+    const int h = threadIdx.x % S;                 // lane within the group
+    const int groups_per_block = NT / S;
+    const long long gstride = (long long)Q.nblocks * groups_per_block;
+    double accr[NCL], acci[NCL], fullr = 0.0, fulli = 0.0;
+#pragma unroll
+    for (int j = 0; j < NCL; j++)
+        accr[j] = acci[j] = 0.0;
+
+    // All lanes of a warp run the same number of iterations (the group shuffles
+    // below need the full warp); lanes past the last segment redo the last one
+    // with weight 0.
+    const int group_in_warp = (threadIdx.x & 31) / S;
+    for (long long seg0 = (long long)((int)blockIdx.x - Q.first_block) * groups_per_block +
+                          threadIdx.x / S;
+         seg0 - group_in_warp < Q.nseg; seg0 += gstride) {
+        const bool valid = seg0 < Q.nseg;
+        const long long seg = valid ? seg0 : Q.nseg - 1;
+        // ---- seed (same bookkeeping as seed_segment in pqperm_walk.cuh)
+        double sr[NCL], si[NCL];
+#pragma unroll
+        for (int j = 0; j < NCL; j++) {
+            const double2 a = smA[j * S + h];
+            sr[j] = a.x;
+            si[j] = a.y;
+        }
+        int odd = 0;
+        double bin = 1.0;
+        {
+            uint8_t chain[kMaxDigits];
+            unsigned long long rest = (unsigned long long)seg;
+            for (int d = q; d < D; ++d) {
+                const unsigned L = Q.mult[d] + 1u;
+                if (rest >> 32) {
+                    chain[d] = (uint8_t)(rest % L);
+                    rest /= L;
+                } else {
+                    const unsigned r32 = (unsigned)rest;
+                    chain[d] = (uint8_t)(r32 % L);
+                    rest = r32 / L;
+                }
+            }
+            for (int d = D - 1; d >= q; --d) {
+                const int r = Q.mult[d];
+                const int g = odd ? r - chain[d] : chain[d];
+                odd ^= (g & 1);
+                if (g != 0 && g != r)
+                    bin *= small_binom(r, g);
+                const double w = 0.5 * (double)(r - 2 * g);
+                const double2 *row = smA + (d + 1) * NCP + h;
+#pragma unroll
+                for (int j = 0; j < NCL; j++) {
+                    const double2 a = row[j * S];
+                    sr[j] = __fma_rn(w, a.x, sr[j]);
+                    si[j] = __fma_rn(w, a.y, si[j]);
+                }
+            }
+        }
+        unsigned dirmask = 0;
+        for (int d = q - 1; d >= 0; --d) {
+            const int r = Q.mult[d];
+            dirmask |= (unsigned)odd << d;
+            const double w = odd ? -0.5 * (double)r : 0.5 * (double)r;
+            const double2 *row = smA + (d + 1) * NCP + h;
+#pragma unroll
+            for (int j = 0; j < NCL; j++) {
+                const double2 a = row[j * S];
+                sr[j] = __fma_rn(w, a.x, sr[j]);
+                si[j] = __fma_rn(w, a.y, si[j]);
+            }
+            if (r & 1)
+                odd = 0;
+        }
+        const double factor = valid ? (odd ? -bin : bin) : 0.0;
+
+        // ---- walk
+        for (int m = 0; m < W; ++m) {
+            if (m != 0) {
+                const int p = s_sched[m];
+                const double sg = ((dirmask >> p) & 1u) ? 1.0 : -1.0;
+                dirmask ^= (1u << p) - 1u;
+                const double2 *row = smA + (p + 1) * NCP + h;
+#pragma unroll
+                for (int j = 0; j < NCL; j++) {
+                    const double2 a = row[j * S];
+                    sr[j] = __fma_rn(sg, a.x, sr[j]);
+                    si[j] = __fma_rn(sg, a.y, si[j]);
+                }
+            }
+            const double w = factor * s_wtab[m];
+
+            // suffix products of this lane's columns: sufr[j] = prod_{k >= j} s_k^{c_k}
+            double sufr[NCL + 1], sufi[NCL + 1];
+            sufr[NCL] = 1.0;
+            sufi[NCL] = 0.0;
+#pragma unroll
+            for (int j = NCL - 1; j >= 0; j--) {
+                double tr = sufr[j + 1], ti = sufi[j + 1];
+                if (UNITCOLS) {
+                    if (j == NCL - 1) {
+                        tr = sr[j];
+                        ti = si[j];
+                    } else {
+                        cmul(tr, ti, sr[j], si[j]);
+                    }
+                } else {
+                    const int c = Q.colmult[j * S + h];
+                    for (int k = 0; k < c; k++)
+                        cmul(tr, ti, sr[j], si[j]);
+                }
+                sufr[j] = tr;
+                sufi[j] = ti;
+            }
+            // product of the columns owned by the other lanes of the group
+            double prer = 1.0, prei = 0.0;
+            if (S > 1) {
+                bool first = true;
+#pragma unroll
+                for (int x = 1; x < S; x++) {
+                    const double orr = __shfl_xor_sync(0xffffffffu, sufr[0], x);
+                    const double oi = __shfl_xor_sync(0xffffffffu, sufi[0], x);
+                    if (first) {
+                        prer = orr;
+                        prei = oi;
+                        first = false;
+                    } else {
+                        cmul(prer, prei, orr, oi);
+                    }
+                }
+            }
+            // prefix pass: P_j = pre * s_j^{c_j - 1} * suf_{j+1}
+#pragma unroll
+            for (int j = 0; j < NCL; j++) {
+                double pr = prer, pi = prei;
+                if (UNITCOLS) {
+                    if (j + 1 < NCL)
+                        cmul(pr, pi, sufr[j + 1], sufi[j + 1]);
+                    accr[j] = __fma_rn(w, pr, accr[j]);
+                    acci[j] = __fma_rn(w, pi, acci[j]);
+                    cmul(prer, prei, sr[j], si[j]);
+                } else {
+                    const int c = Q.colmult[j * S + h];
+                    for (int k = 0; k < c - 1; k++)
+                        cmul(pr, pi, sr[j], si[j]);
+                    double fr = pr, fi = pi; // pre * s_j^{c_j - 1}
+                    cmul(pr, pi, sufr[j + 1], sufi[j + 1]);
+                    accr[j] = __fma_rn(w, pr, accr[j]);
+                    acci[j] = __fma_rn(w, pi, acci[j]);
+                    cmul(fr, fi, sr[j], si[j]);
+                    prer = fr;
+                    prei = fi;
+                }
+            }
+            fullr = __fma_rn(w, prer, fullr); // all columns: what a c_l = 0 column receives
+            fulli = __fma_rn(w, prei, fulli);
+        }
+    }
+
+    // ---- CTA reduction: lanes with equal h hold the same columns
+    __shared__ double red[(NT / 32) * (NCP + 1) * 2];
+#pragma unroll
+    for (int j = 0; j < NCL; j++) {
+#pragma unroll
+        for (int delta = 16; delta >= S; delta >>= 1) {
+            accr[j] += __shfl_down_sync(0xffffffffu, accr[j], delta);
+            acci[j] += __shfl_down_sync(0xffffffffu, acci[j], delta);
+        }
+    }
+#pragma unroll
+    for (int delta = 16; delta >= S; delta >>= 1) {
+        fullr += __shfl_down_sync(0xffffffffu, fullr, delta);
+        fulli += __shfl_down_sync(0xffffffffu, fulli, delta);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < S) {
+        double *dst = red + warp * (NCP + 1) * 2;
+#pragma unroll
+        for (int j = 0; j < NCL; j++) {
+            dst[(j * S + lane) * 2] = accr[j];
+            dst[(j * S + lane) * 2 + 1] = acci[j];
+        }
+        if (lane == 0) {
+            dst[NCP * 2] = fullr;
+            dst[NCP * 2 + 1] = fulli;
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < NCP + 1; k += NT) {
+        double re = 0.0, im = 0.0;
+        for (int w = 0; w < NT / 32; w++) {
+            re += red[(w * (NCP + 1) + k) * 2];
+            im += red[(w * (NCP + 1) + k) * 2 + 1];
+        }
+        P.partials[(size_t)blockIdx.x * (NCP + 1) + k] = make_double2(re, im);
+    }
+}
+
+// One warp per problem: sum the problem's CTA partials in CTA order, scale by
+// 2^-(sum_rows - 1) (src/permanent_laplace.cpp:226-235).
+static __global__ void __launch_bounds__(128) laplace_reduce_kernel(const LapParams P, int ncp1)
+{
+    const int prob = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (prob >= P.nprob)
+        return;
+    const LapProblem &Q = P.prob[prob];
+    const double scale = scalbn(1.0, -Q.exp2);
+    for (int k = threadIdx.x & 31; k < ncp1; k += 32) {
+        double re = 0.0, im = 0.0;
+        for (int b = 0; b < Q.nblocks; b++) {
+            const double2 v = P.partials[(size_t)(Q.first_block + b) * ncp1 + k];
+            re += v.x;
+            im += v.y;
+        }
+        P.out[(size_t)prob * ncp1 + k] = make_double2(re * scale, im * scale);
+    }
+}
+
+} // namespace pqperm

@@ -42,3 +42,11 @@ cudaError_t launch_dfma_probe(int num_sms, int iters, double *sink, cudaStream_t
                               double *flops);
 
 } // namespace pqperm
+
+namespace pqperm {
+
+cudaError_t launch_laplace(int S, int NCL, bool unitcols, const LapParams &P,
+                           int total_blocks, size_t smem, cudaStream_t stream);
+cudaError_t launch_laplace_reduce(const LapParams &P, int ncp1, cudaStream_t stream);
+
+} // namespace pqperm

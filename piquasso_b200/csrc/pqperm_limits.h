@@ -16,4 +16,22 @@ constexpr int kBinDefaultChains = 2;    // independent product chains
 constexpr int64_t kMaxSegLenBinary = INT64_C(1) << 14;
 constexpr int64_t kMaxSegLenNary = INT64_C(1) << 12;
 
+constexpr int kLapMaxSegLen = 256;     // Laplace: terms per segment (tables in shared memory)
+constexpr int kLapThreads = 128;
+
+// Lane split of the Laplace walk for nc active columns: S lanes per Gray
+// segment, NCL columns per lane (S * NCL >= nc).
+struct LapVariant {
+    int S;
+    int NCL;
+};
+inline LapVariant laplace_variant(int nc)
+{
+    if (nc <= 8)
+        return {1, nc < 1 ? 1 : nc};
+    if (nc <= 26)
+        return {2, (nc + 1) / 2};
+    return {4, (nc + 3) / 4};
+}
+
 } // namespace pqperm

@@ -146,6 +146,10 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
             plan.kernel = 2;
     }
     plan.NCP = plan.kernel == 2 ? plan.NC : (plan.NC <= 4 ? 4 : (plan.NC + 3) / 4 * 4);
+    if (opt.laplace) {
+        const LapVariant v = laplace_variant(plan.NC);
+        plan.NCP = v.S * v.NCL;
+    }
     plan.colmult.resize(plan.NCP, 1);
 
     // ---- where to cut the digits --------------------------------------------
@@ -153,10 +157,15 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
     const double regs = 4.0 * plan.NCP + 48.0;
     double resident = std::floor(65536.0 / regs / 64.0) * 64.0;
     resident = std::max(64.0, std::min(2048.0, resident)) * opt.num_sms;
+    if (opt.laplace) // S lanes per segment; the batch shares the machine
+        resident = std::max(1.0, resident / laplace_variant(plan.NC).S /
+                                     std::max(1, opt.batch));
     const double step = opt.laplace ? (2.0 * plan.NCP + 14.0 * plan.M)
                                     : (2.0 * plan.NCP + 4.0 * plan.M + 2.0);
     const double seed = 2.0 * plan.NCP * (plan.D + 1) + 40.0 * plan.D + 100.0;
-    const int64_t wmax = plan.binary ? kMaxSegLenBinary : kMaxSegLenNary;
+    const int64_t wmax = opt.laplace ? (int64_t)kLapMaxSegLen
+                                     : ((plan.binary && plan.unitcols) ? kMaxSegLenBinary
+                                                                       : kMaxSegLenNary);
     const int qmin = plan.kernel == 2 ? plan.B : 0;
     int best_q = -1;
     double best_cost = 0.0;
@@ -204,7 +213,7 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
         for (int g = 0; g <= plan.mult[d]; g++)
             plan.binom.push_back(binom_d(plan.mult[d], g));
     }
-    if (!plan.binary) {
+    if (!(plan.binary && plan.unitcols) && !opt.laplace) {
         // step m-1 -> m of the low counter: which digit moves, and the weight
         // (-1)^m prod_{d<q} C(r_d, c_d(m)) (C(r,g) = C(r,r-g): the reflection
         // of a digit does not change its binomial).

@@ -25,6 +25,26 @@
 
 namespace pqperm {
 
+// ---- dynamic segment distribution -------------------------------------------
+// The warp schedulers do not share issue slots fairly between resident warps:
+// with a static split the favoured warp of each SM sub-partition finishes at
+// ~2/3 of the run and its partner runs alone (profiles/round1: 6.6 of 8 warps
+// active on average, FP64 pipe 72%).  Instead every warp draws batches of 32
+// consecutive segments from one global counter, so all warps stay busy until
+// the segment range is exhausted.  Returns this lane's segment, or -1 when the
+// range is exhausted (warp-uniform); the value may be >= P.seg_end in the last
+// batch.
+__device__ __forceinline__ long long next_batch(const WalkParams &P)
+{
+    unsigned long long base = 0;
+    if ((threadIdx.x & 31) == 0)
+        base = atomicAdd(P.counter, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((long long)base >= P.seg_end - P.seg_begin)
+        return -1;
+    return P.seg_begin + (long long)base + (threadIdx.x & 31);
+}
+
 // ---- seeding: s_j, direction mask and weight of term(seg * W) ---------------
 // Restates the seed of src/permanent.cpp:174-202 for offset = seg * W.
 template <int NC, bool BINARY>
@@ -175,10 +195,14 @@ __global__ void __launch_bounds__(NT) perm_walk_generic(const __grid_constant__ 
     __syncthreads();
 
     dd totre{0.0, 0.0}, totim{0.0, 0.0};
-    const long long stride = (long long)gridDim.x * NT;
     const int W = (int)P.W;
-    for (long long seg = P.seg_begin + (long long)blockIdx.x * NT + threadIdx.x;
-         seg < P.seg_end; seg += stride) {
+    for (;;) {
+        // dynamic distribution: a warp takes the next 32 segments (see next_batch)
+        const long long seg = next_batch(P);
+        if (seg < 0)
+            break;
+        if (seg >= P.seg_end)
+            continue;
         double sr[NC], si[NC];
         unsigned dirmask;
         double factor;
@@ -245,10 +269,13 @@ __global__ void __launch_bounds__(NT) perm_walk_binary(const __grid_constant__ W
     const double2 *smA = PQ_BINARY_CONST_MATRIX;
 
     dd totre{0.0, 0.0}, totim{0.0, 0.0};
-    const long long stride = (long long)gridDim.x * NT;
     const int nblk = (int)(P.W >> B);
-    for (long long seg = P.seg_begin + (long long)blockIdx.x * NT + threadIdx.x;
-         seg < P.seg_end; seg += stride) {
+    for (;;) {
+        const long long seg = next_batch(P);
+        if (seg < 0)
+            break;
+        if (seg >= P.seg_end)
+            continue;
         double sr[NC], si[NC];
         unsigned dirmask;
         double factor;
