@@ -133,6 +133,23 @@ typedef struct pq_plan_info {
     double flops_per_term; /* 2*C + 6*M + 2 */
 } pq_plan_info;
 
+/* ---------------------------------------------------------------------
+ * Resident jobs: the same partitioned permanent with the inputs uploaded
+ * ONCE (create) and the kernels launched any number of times (launch), e.g.
+ * to time the kernels with the inputs already in HBM.  One job is resident
+ * per device; a job evicted by another call re-uploads itself on launch.
+ * status / trivial as for pq_perm_partial_c128 (*job stays NULL when the
+ * problem is trivial).
+ * ------------------------------------------------------------------- */
+typedef struct pq_perm_job pq_perm_job;
+int pq_perm_job_create_c128(const double *A, int R, int C, const int32_t *rows,
+                            const int32_t *cols, int part, int nparts, int device,
+                            pq_perm_job **job, int *status, double trivial[2]);
+int pq_perm_job_launch(pq_perm_job *job, void *stream, double *d_partial);
+int pq_perm_job_info(const pq_perm_job *job, pq_plan_info *info);
+int64_t pq_perm_job_terms(const pq_perm_job *job); /* Gray-code terms this rank walks */
+int pq_perm_job_destroy(pq_perm_job *job);
+
 /* Plan that pq_perm_c128 would use for these multiplicities (no GPU needed). */
 int pq_perm_plan(int R, int C, const int32_t *rows, const int32_t *cols,
                  pq_plan_info *info);
@@ -156,6 +173,11 @@ int pq_perm_segment_sums_c128(const double *A, int R, int C,
 /* Kernel-only duration (ms, CUDA events on the library stream) of the last
  * pq_perm_c128 / pq_perm_laplace* call made on `device`; -1 if none. */
 double pq_last_kernel_ms(int device);
+
+/* Durations (ms, CUDA events on the launching stream) of the most recent
+ * walk+reduce launches on `device`, newest first; returns how many were
+ * written.  The stream they ran on must have been synchronised. */
+int pq_kernel_ms_history(int device, double *out, int max);
 
 /* Number of kernels the library has launched on all devices since load. */
 int64_t pq_launch_count(void);

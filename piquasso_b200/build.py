@@ -102,5 +102,36 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_pybind(force: bool = False, verbose: bool = False) -> str:
+    """The pybind11 drop-in module ``permanent`` (same name and overloads as the
+    reference's ``piquasso/_math/permanent*.so``), linked against libpqperm.so
+    with an $ORIGIN rpath; lands in ``piquasso_b200/native/``."""
+    import sysconfig
+
+    import pybind11
+
+    build(force=force, verbose=verbose)
+    out_dir = os.path.join(HERE, "native")
+    os.makedirs(out_dir, exist_ok=True)
+    suffix = sysconfig.get_config_var("EXT_SUFFIX")
+    target = os.path.join(out_dir, "permanent" + suffix)
+    src = os.path.join(CSRC, "pybind_permanent.cpp")
+    hdr = os.path.join(HERE, "..", "include", "pqperm.h")
+    if (not force and os.path.exists(target)
+            and os.path.getmtime(target) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        return target
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
+    cmd = [gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden",
+           "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"],
+           src, "-o", target, "-L", HERE, "-lpqperm", "-Wl,-rpath,$ORIGIN/.."]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("pybind build failed:\n%s\n%s" % (proc.stdout, proc.stderr))
+    if verbose:
+        print("pybind module:", target)
+    return target
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
+    build_pybind(force="--force" in sys.argv, verbose=True)

@@ -83,6 +83,7 @@ extern "C" const char *pq_last_error(void) { return g_last_error.c_str(); }
 namespace pqperm {
 
 constexpr int kMaxGrid = 148 * 32 * 2;
+constexpr int kTimingRing = 64;
 
 struct DeviceCtx {
     int device = -1;
@@ -101,6 +102,9 @@ struct DeviceCtx {
     double *h_pinned = nullptr;    // staging: A2 + out
     double last_kernel_ms = -1.0;
     bool ready = false;
+    uint64_t resident_job = 0;     // id of the pq_perm_job whose inputs sit in the buffers
+    cudaEvent_t ring0[kTimingRing], ring1[kTimingRing];  // event pairs around the kernels
+    uint64_t ring_next = 0;
     // growable buffers of the batched Laplace path
     void *d_lap[4] = {nullptr, nullptr, nullptr, nullptr};   // prob, A2, partials, out
     size_t d_lap_cap[4] = {0, 0, 0, 0};
@@ -143,6 +147,10 @@ static int ctx_get(int device, DeviceCtx **out)
         PQ_CUDA(cudaEventCreate(&c->ev0));
         PQ_CUDA(cudaEventCreate(&c->ev1));
         PQ_CUDA(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+        for (int i = 0; i < kTimingRing; i++) {
+            PQ_CUDA(cudaEventCreate(&c->ring0[i]));
+            PQ_CUDA(cudaEventCreate(&c->ring1[i]));
+        }
         PQ_CUDA(cudaMalloc(&c->d_A2, kA2Doubles * sizeof(double)));
         PQ_CUDA(cudaMalloc(&c->d_partials, (size_t)kMaxGrid * 4 * sizeof(double)));
         PQ_CUDA(cudaMalloc(&c->d_out, 4 * sizeof(double)));
@@ -181,24 +189,17 @@ static void fill_params(const Plan &plan, DeviceCtx *c, WalkParams &P)
 
 // Enqueue upload + walk + reduction of segments [seg_begin, seg_end) on c's
 // stream; the four-double partial lands in d_dst (device) on that stream.
-static int enqueue_walk(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64_t seg_end,
-                        double *d_dst, double *d_segsums, cudaStream_t stream)
+// Stage the plan's matrix and tables into c's device buffers on `stream`.
+static int upload_plan(const Plan &plan, DeviceCtx *c, cudaStream_t stream)
 {
-    WalkParams P;
-    fill_params(plan, c, P);
-    P.seg_begin = seg_begin;
-    P.seg_end = seg_end;
-    P.segsums = d_segsums;
-
-    // the pinned staging buffer may still feed the previous (caller-stream) enqueue
+    // the pinned staging buffer may still feed the previous (caller-stream) upload
     if (c->up_pending) {
         PQ_CUDA(cudaEventSynchronize(c->ev_up));
         c->up_pending = false;
     }
+    c->resident_job = 0;
     const size_t a2_bytes = plan.A2.size() * sizeof(double);
     std::memcpy(c->h_pinned, plan.A2.data(), a2_bytes);
-    LaunchInfo info;
-    cudaError_t e;
     PQ_CUDA(cudaMemcpyAsync(c->d_A2, c->h_pinned, a2_bytes, cudaMemcpyHostToDevice, stream));
     const bool fast = plan.binary && plan.unitcols; // tables are needed otherwise
     if (!fast && plan.W > 1) {
@@ -211,9 +212,28 @@ static int enqueue_walk(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64
         PQ_CUDA(cudaMemcpyAsync(c->d_binom, plan.binom.data(),
                                 plan.binom.size() * sizeof(double), cudaMemcpyHostToDevice,
                                 stream));
-    PQ_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), stream));
     PQ_CUDA(cudaEventRecord(c->ev_up, stream));
     c->up_pending = true;
+    return PQ_OK;
+}
+
+// Enqueue walk + reduction of segments [seg_begin, seg_end) on `stream`, inputs
+// already resident (upload_plan); the four-double partial lands in d_dst.  The
+// kernels are bracketed by an event pair of the timing ring.
+static int launch_plan(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64_t seg_end,
+                       double *d_dst, double *d_segsums, cudaStream_t stream)
+{
+    WalkParams P;
+    fill_params(plan, c, P);
+    P.seg_begin = seg_begin;
+    P.seg_end = seg_end;
+    P.segsums = d_segsums;
+    LaunchInfo info;
+    cudaError_t e;
+    const bool fast = plan.binary && plan.unitcols;
+    PQ_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), stream));
+    const int slot = (int)(c->ring_next % kTimingRing);
+    PQ_CUDA(cudaEventRecord(c->ring0[slot], stream));
     if (plan.kernel == 2) {
         e = launch_binary(plan.NC, plan.B, plan.chains, P,
                           reinterpret_cast<const double2 *>(c->d_A2),
@@ -226,8 +246,19 @@ static int enqueue_walk(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64
     e = launch_reduce_partials(c->d_partials, info.grid, d_dst, stream);
     if (e != cudaSuccess)
         return fail_cuda(e, "launch reduce_partials");
+    PQ_CUDA(cudaEventRecord(c->ring1[slot], stream));
+    c->ring_next++;
     g_launches += 2;
     return PQ_OK;
+}
+
+static int enqueue_walk(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64_t seg_end,
+                        double *d_dst, double *d_segsums, cudaStream_t stream)
+{
+    const int rc = upload_plan(plan, c, stream);
+    if (rc)
+        return rc;
+    return launch_plan(plan, c, seg_begin, seg_end, d_dst, d_segsums, stream);
 }
 
 static PlanOptions plan_options(int num_sms)
@@ -578,6 +609,138 @@ extern "C" double pq_fp64_peak_tflops(int device, int iters)
             best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
     return best;
+}
+
+// ---------------------------------------------------------------------------
+// resident jobs: inputs uploaded once, kernels launched many times
+// ---------------------------------------------------------------------------
+struct pq_perm_job {
+    uint64_t id;
+    int device;
+    Plan plan;
+    int64_t seg_begin, seg_end;
+};
+static std::atomic<uint64_t> g_job_ids{1};
+
+extern "C" int pq_perm_job_create_c128(const double *A, int R, int C, const int32_t *rows,
+                                       const int32_t *cols, int part, int nparts, int device,
+                                       pq_perm_job **job, int *status, double trivial[2])
+{
+    if (!job || nparts < 1 || part < 0 || part >= nparts)
+        return fail(PQ_ERR_BAD_ARG, "bad job arguments");
+    *job = nullptr;
+    std::lock_guard<std::mutex> lock(g_mu);
+    std::unique_ptr<pq_perm_job> j(new pq_perm_job());
+    std::string err;
+    {
+        PlanOptions o = plan_options(148);
+        const int rc = make_plan(nullptr, R, C, rows, cols, o, j->plan, err);
+        if (rc)
+            return fail(rc, err);
+        if (j->plan.trivial) {
+            if (status)
+                *status = 1;
+            if (trivial) {
+                trivial[0] = j->plan.triv[0];
+                trivial[1] = j->plan.triv[1];
+            }
+            return PQ_OK;
+        }
+    }
+    DeviceCtx *c = nullptr;
+    int rc = ctx_get(device, &c);
+    if (rc)
+        return rc;
+    PlanOptions o = plan_options(c->num_sms * nparts);
+    rc = make_plan(A, R, C, rows, cols, o, j->plan, err);
+    if (rc)
+        return fail(rc, err);
+    j->id = g_job_ids++;
+    j->device = device;
+    split_range(j->plan.nseg, part, nparts, &j->seg_begin, &j->seg_end);
+    rc = upload_plan(j->plan, c, c->stream);
+    if (rc)
+        return rc;
+    PQ_CUDA(cudaStreamSynchronize(c->stream));
+    c->resident_job = j->id;
+    if (status)
+        *status = 0;
+    *job = j.release();
+    return PQ_OK;
+}
+
+extern "C" int pq_perm_job_launch(pq_perm_job *job, void *stream, double *d_partial)
+{
+    if (!job || !d_partial)
+        return fail(PQ_ERR_BAD_ARG, "null job or output");
+    std::lock_guard<std::mutex> lock(g_mu);
+    DeviceCtx *c = nullptr;
+    int rc = ctx_get(job->device, &c);
+    if (rc)
+        return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    if (c->resident_job != job->id) { // evicted by another call on this device
+        rc = upload_plan(job->plan, c, s);
+        if (rc)
+            return rc;
+        c->resident_job = job->id;
+    }
+    if (job->seg_begin < job->seg_end) {
+        rc = launch_plan(job->plan, c, job->seg_begin, job->seg_end, d_partial, nullptr, s);
+        if (rc)
+            return rc;
+    } else {
+        PQ_CUDA(cudaMemsetAsync(d_partial, 0, 4 * sizeof(double), s));
+    }
+    if (!stream)
+        PQ_CUDA(cudaStreamSynchronize(s));
+    return PQ_OK;
+}
+
+extern "C" int pq_perm_job_info(const pq_perm_job *job, pq_plan_info *info)
+{
+    if (!job || !info)
+        return fail(PQ_ERR_BAD_ARG, "null job or info");
+    fill_info(job->plan, info);
+    return PQ_OK;
+}
+
+extern "C" int64_t pq_perm_job_terms(const pq_perm_job *job)
+{
+    return job ? (job->seg_end - job->seg_begin) * job->plan.W : 0;
+}
+
+extern "C" int pq_perm_job_destroy(pq_perm_job *job)
+{
+    if (!job)
+        return PQ_OK;
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (job->device >= 0 && job->device < (int)g_ctx.size() && g_ctx[job->device] &&
+        g_ctx[job->device]->resident_job == job->id)
+        g_ctx[job->device]->resident_job = 0;
+    delete job;
+    return PQ_OK;
+}
+
+// Durations (ms) of the most recent walk+reduce launches on `device`, newest
+// first; the caller must have synchronised the stream they ran on.
+extern "C" int pq_kernel_ms_history(int device, double *out, int max)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (device < 0 || device >= (int)g_ctx.size() || !g_ctx[device] || !out || max < 1)
+        return 0;
+    DeviceCtx *c = g_ctx[device].get();
+    int n = 0;
+    for (uint64_t k = c->ring_next; k > 0 && n < max && n < kTimingRing; k--) {
+        const int slot = (int)((k - 1) % kTimingRing);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ring0[slot], c->ring1[slot]) != cudaSuccess) {
+            cudaGetLastError();
+            break;
+        }
+        out[n++] = ms;
+    }
+    return n;
 }
 
 // ---------------------------------------------------------------------------

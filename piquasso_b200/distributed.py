@@ -1,0 +1,79 @@
+"""One permanent over several GPUs, one process per GPU.
+
+The Gray-code term space is cut into equal segments (``plan.plan``); rank g of
+G walks the contiguous segment range ``plan.segment_range(nseg, g, G)`` with
+the same kernels as the single-GPU call and leaves an UNSCALED double-double
+partial (re_hi, re_lo, im_hi, im_lo) in its own HBM.  The only exchange step
+of the path is ONE all-reduce (sum) of those four doubles -- NCCL over
+NVLink/NVSwitch when the process group is NCCL -- after which every rank holds
+the permanent.  The payload is 32 bytes: the collective is latency-bound, there
+is nothing to overlap, and the reference has no counterpart (its parallelism
+is one OpenMP loop, src/permanent.cpp:152-155).
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._math.permanent import _check_shapes, _raise, _resolve_matrix, _resolve_mult
+
+
+def _device_partial(a, r, c, part, nparts, device_index):
+    """Enqueue this rank's partial on the current torch stream; returns the
+    (4,) float64 CUDA tensor, or a complex for a reference early-out."""
+    import torch
+
+    lib = _lib.load()
+    out = torch.zeros(4, dtype=torch.float64, device="cuda:%d" % device_index)
+    stream = torch.cuda.current_stream(device_index).cuda_stream
+    status = ctypes.c_int(0)
+    triv = np.zeros(2)
+    rc = lib.pq_perm_partial_c128(
+        a.ctypes.data_as(_lib.c_double_p), a.shape[0], a.shape[1],
+        r.ctypes.data_as(_lib.c_int32_p), c.ctypes.data_as(_lib.c_int32_p),
+        part, nparts, device_index, ctypes.c_void_p(stream),
+        ctypes.c_void_p(out.data_ptr()), ctypes.byref(status),
+        triv.ctypes.data_as(_lib.c_double_p))
+    _raise(rc)
+    if status.value == 1:
+        return complex(triv[0], triv[1])
+    return out
+
+
+def finish(partial4, sum_rows):
+    """(hi+lo) * 2^-(sum_rows-1), src/permanent.cpp:259."""
+    lib = _lib.load()
+    p = np.ascontiguousarray(np.asarray(partial4, dtype=np.float64))
+    out = np.zeros(2)
+    _lib.check(lib.pq_perm_finish(p.ctypes.data_as(_lib.c_double_p), int(sum_rows),
+                                  out.ctypes.data_as(_lib.c_double_p)))
+    return complex(out[0], out[1])
+
+
+def permanent_allreduce(matrix, rows, cols, group=None, device_index=None):
+    """``permanent(matrix, rows, cols)`` computed by every rank of ``group``
+    together; all ranks return the same 0-d complex128 array.
+
+    Must be called by all ranks with identical arguments."""
+    import torch
+    import torch.distributed as dist
+
+    a = np.ascontiguousarray(_resolve_matrix(matrix), dtype=np.complex128)
+    r = _resolve_mult(rows, "rows")
+    c = _resolve_mult(cols, "cols")
+    _check_shapes(a, r, c)
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    if device_index is None:
+        device_index = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    part = _device_partial(a, r, c, rank, world, device_index)
+    if isinstance(part, complex):
+        return np.array(np.complex128(part))
+    if world > 1:
+        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+    return np.array(np.complex128(finish(part.cpu().numpy(), int(r.sum()))))

@@ -80,7 +80,8 @@ def _to_first_quantized(occupation):
     return np.array(out, dtype=int)
 
 
-def generate_samples(input, shots, interferometer, seed_sequence, batch_shots=None):
+def generate_samples(input, shots, interferometer, seed_sequence, reject_condition=None,
+                     batch_shots=None):
     """Clifford & Clifford algorithm B, all shots in lock step.
 
     Restates ``_generate_samples`` / ``_generate_sample`` / ``_calculate_pmf``
@@ -89,6 +90,11 @@ def generate_samples(input, shots, interferometer, seed_sequence, batch_shots=No
     shots.  Shot ``idx`` owns ``np.random.default_rng(seed_sequence + idx)`` and
     draws ``choice(len(to_shrink))`` then ``choice(arange(d), p=pmf)`` per photon
     exactly as the reference does, so the returned tuples are identical.
+
+    ``reject_condition`` (uniform losses, ``simulation_steps.py:350-360``) is a
+    state-independent callable the reference evaluates once per photon per shot
+    in shot-major order, possibly drawing from a shared generator; it is
+    therefore evaluated up front in that same order.
     """
     input = np.asarray(input, dtype=int)
     U = np.ascontiguousarray(interferometer, dtype=np.complex128)
@@ -97,6 +103,11 @@ def generate_samples(input, shots, interferometer, seed_sequence, batch_shots=No
     first_quantized = _to_first_quantized(input)
     if batch_shots is None:
         batch_shots = shots
+    if reject_condition is None:
+        rejected = np.zeros((shots, n), dtype=bool)
+    else:
+        rejected = np.array([[bool(reject_condition()) for _ in range(n)]
+                             for _ in range(shots)], dtype=bool).reshape(shots, n)
     samples_all = []
     for start in range(0, shots, max(1, batch_shots)):
         stop = min(shots, start + max(1, batch_shots))
@@ -106,9 +117,10 @@ def generate_samples(input, shots, interferometer, seed_sequence, batch_shots=No
         current_input = np.zeros((nb, d), dtype=int)
         to_shrink = [np.copy(first_quantized) for _ in range(nb)]
         arange_d = np.arange(d)
-        for _ in range(1, n + 1):
+        for photon in range(n):
             mats, rws, cls, nz = [], [], [], []
-            for s in range(nb):
+            live = [s for s in range(nb) if not rejected[start + s, photon]]
+            for s in live:
                 # _grow_current_input (sampling.py:197-205)
                 ridx = rngs[s].choice(len(to_shrink[s]))
                 mode = to_shrink[s][ridx]
@@ -122,10 +134,10 @@ def generate_samples(input, shots, interferometer, seed_sequence, batch_shots=No
                 cls.append(current_input[s][in_nz])
                 nz.append(arange_d[in_nz])
             partials = permanent_laplace_batch(mats, rws, cls)
-            for s in range(nb):
+            for i, s in enumerate(live):
                 # _calculate_pmf (sampling.py:736-749): pmf[m] = |sum_j in_j p_j U[m, nz_j]|^2
-                weights = current_input[s][nz[s]] * partials[s]
-                amp = U[:, nz[s]] @ weights
+                weights = current_input[s][nz[i]] * partials[i]
+                amp = U[:, nz[i]] @ weights
                 pmf = np.abs(amp) ** 2
                 pmf = pmf / pmf.sum()
                 index = rngs[s].choice(arange_d, p=pmf)

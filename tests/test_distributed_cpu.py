@@ -1,0 +1,74 @@
+"""The N>1 host path on CPU: two ranks over gloo.
+
+The GPU partial of each rank is stood in for by the oracle's long-double walk
+of exactly the segment range the library assigns to that rank
+(``plan.plan`` + ``plan.segment_range``); everything else -- argument
+resolution, rank -> range mapping, the one all-reduce of four doubles, the
+final scaling -- is the product code path of ``piquasso_b200.distributed``.
+"""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from conftest import haar
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _oracle_partial(a, r, c, part, nparts, device_index):
+    from piquasso_b200 import plan
+    p = plan.plan(r, c)
+    if p["trivial"]:
+        return complex(1.0, 0.0)
+    b, e = plan.segment_range(p["nseg"], part, nparts)
+    _, quads, _ = oracle.partial(a, r, c, b * p["seg_len"], e * p["seg_len"])
+    return torch.tensor(quads[0], dtype=torch.float64)
+
+
+def _worker(rank, world, port, cases, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from piquasso_b200 import distributed
+    distributed._device_partial = _oracle_partial
+    out = []
+    for a, rows, cols in cases:
+        out.append(complex(distributed.permanent_allreduce(a, rows, cols, device_index=0)))
+    results[rank] = out
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_ranks_gloo_sum_to_the_permanent():
+    rng = np.random.default_rng(41)
+    cases = [(haar(11, 11), np.ones(11, np.int32), np.ones(11, np.int32)),
+             (haar(3, 2), np.zeros(3, np.int32), np.zeros(3, np.int32))]
+    for trial in range(4):
+        d = int(rng.integers(2, 7))
+        nph = int(rng.integers(2, 9))
+        cases.append((haar(d, 50 + trial),
+                      rng.multinomial(nph, np.ones(d) / d).astype(np.int32),
+                      rng.multinomial(nph, np.ones(d) / d).astype(np.int32)))
+    world = 2
+    manager = mp.Manager()
+    results = manager.dict()
+    mp.spawn(_worker, args=(world, _free_port(), cases, results), nprocs=world, join=True)
+    assert set(results.keys()) == {0, 1}
+    for i, (a, rows, cols) in enumerate(cases):
+        want = oracle.permanent(a, rows, cols, precision=1)
+        for rank in range(world):
+            got = results[rank][i]
+            assert abs(got - want) <= 1e-12 * max(abs(want), 1e-3), (i, rank, got, want)
+        assert results[0][i] == results[1][i]  # every rank holds the same value

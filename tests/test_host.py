@@ -1,0 +1,165 @@
+"""Host-side logic, no kernel launches: ABI surface, planning, Gray
+enumeration, overload resolution and error behaviour of the Python mirror."""
+
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ROOT, haar
+from piquasso_b200 import _lib, plan
+from piquasso_b200._math.permanent import permanent, permanent_laplace
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "pqperm.h")).read()
+    declared = set(re.findall(r"\b(pq_[a-z0-9_]+)\s*\(", header))
+    declared.discard("pq_plan_info")
+    bound = {name for name, _, _ in _lib.SIGNATURES}
+    assert declared == bound, declared ^ bound
+    for name in declared:
+        assert hasattr(lib, name)
+
+
+def test_plan_all_ones():
+    for n in (2, 5, 20, 30, 40):
+        p = plan.plan(np.ones(n, int), np.ones(n, int))
+        assert p["idx_max"] == 2 ** (n - 1)      # src/permanent.cpp:131-142
+        assert p["nseg"] * p["seg_len"] == p["idx_max"]
+        assert p["active_rows"] == n - 1 and p["active_cols"] == n
+        assert p["flops_per_term"] == 8 * n + 2
+        assert p["sum_rows"] == n and p["trivial"] == 0
+    assert plan.plan(np.ones(40, int), np.ones(40, int))["kernel"] == 2
+    assert plan.plan([2, 1, 0, 3], [1, 1, 4, 0])["kernel"] == 1
+
+
+def test_plan_idx_max_matches_oracle():
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        d = int(rng.integers(1, 9))
+        n = int(rng.integers(1, 12))
+        rows = rng.multinomial(n, np.ones(d) / d)
+        cols = rng.multinomial(n, np.ones(d) / d)
+        p = plan.plan(rows, cols)
+        _, _, idx_max = oracle.gray_of_offset(rows, 0)
+        assert p["idx_max"] == idx_max
+        assert p["nseg"] * p["seg_len"] == idx_max
+
+
+def test_plan_trivial_and_errors(lib):
+    assert plan.plan([0, 0, 0], [0, 0, 0])["trivial"] == 1
+    assert plan.plan([], [])["trivial"] == 1
+    with pytest.raises(_lib.PqPermError) as e:
+        plan.plan([1, 1], [1, 0])
+    assert e.value.code == _lib.PQ_ERR_SUM_MISMATCH
+    with pytest.raises(_lib.PqPermError) as e:
+        plan.plan(np.ones(70, int), np.ones(70, int))
+    assert e.value.code == _lib.PQ_ERR_TOO_LARGE
+    with pytest.raises(_lib.PqPermError) as e:
+        plan.plan([-1, 2], [1, 0])
+    assert e.value.code == _lib.PQ_ERR_BAD_ARG
+
+
+def test_gray_enumeration_matches_oracle():
+    """Identical Gray-code term enumeration: offset -> digits, against the
+    restated reference counter (src/n_aryGrayCodeCounter.hpp:170-194)."""
+    rng = np.random.default_rng(11)
+    for _ in range(60):
+        d = int(rng.integers(1, 9))
+        n = int(rng.integers(1, 14))
+        rows = rng.multinomial(n, np.ones(d) / d)
+        _, _, idx_max = oracle.gray_of_offset(rows, 0)
+        for off in {0, idx_max - 1, *rng.integers(0, idx_max, size=6).tolist()}:
+            want, _, _ = oracle.gray_of_offset(rows, int(off))
+            got = plan.gray_of_offset(rows, int(off))
+            assert got.tolist() == want.tolist(), (rows, off)
+
+
+def test_gray_enumeration_beyond_2_pow_31():
+    """The reference truncates offsets to int (n_aryGrayCodeCounter.hpp:179);
+    the 64-bit restatement and the GPU path's host mirror agree above it."""
+    rows = np.ones(40, int)
+    for off in (2 ** 31, 2 ** 31 + 12345, 2 ** 38 + 7, 2 ** 39 - 1):
+        want, _, idx_max = oracle.gray_of_offset(rows, off)
+        assert idx_max == 2 ** 39
+        assert plan.gray_of_offset(rows, off).tolist() == want.tolist()
+        # binary reflected code: g = c ^ (c >> 1) on digits 1..39 (digit 0 is the
+        # radix-1 digit left by the row split)
+        g = off ^ (off >> 1)
+        assert want[0] == 0 and all(int(want[i + 1]) == (g >> i) & 1 for i in range(39))
+
+
+def test_segment_ranges_tile_the_term_space():
+    for nseg in (1, 7, 1024, 2 ** 25 + 3):
+        for nparts in (1, 2, 3, 8):
+            edges = [plan.segment_range(nseg, g, nparts) for g in range(nparts)]
+            assert edges[0][0] == 0 and edges[-1][1] == nseg
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(nparts - 1))
+            sizes = [e - b for b, e in edges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_early_outs_need_no_device_and_keep_dtype():
+    """src/permanent.cpp:106-108 / src/permanent_laplace.cpp:52-57."""
+    z3 = np.zeros(3, int)
+    for dtype in (np.complex64, np.complex128):
+        v = permanent(np.ones((3, 3), dtype=dtype), rows=z3, cols=z3)
+        assert v.shape == () and v.dtype == dtype and v == 1
+    v = permanent(np.ones((3, 3)), z3, z3)            # float64 -> complex128 overload
+    assert v.dtype == np.complex128
+    v = permanent(np.ones((3, 3), dtype=np.float32), z3, z3)  # float32 -> complex64 overload
+    assert v.dtype == np.complex64
+    lp = permanent_laplace(np.ones((0, 0), dtype=np.complex128), [], [])
+    assert lp.shape == (1,) and lp[0] == 1
+    lp = permanent_laplace(np.ones((2, 3), dtype=np.complex128), [0, 0], [1, 0, 0])
+    assert lp.shape == (1,) and lp[0] == 1            # sum(rows) == 0: length-1 result
+
+
+def test_argument_errors():
+    with pytest.raises(RuntimeError):                 # the reference throws too
+        permanent(np.eye(2, dtype=complex), [1, 1], [1, 0])
+    with pytest.raises(ValueError):
+        permanent(np.eye(2, dtype=complex), [1, 1, 1], [1, 1])
+    with pytest.raises(ValueError):
+        permanent(np.ones(4, dtype=complex), [1], [1])
+    with pytest.raises(TypeError):
+        permanent(np.array([["a", "b"], ["c", "d"]]), [1, 1], [1, 1])
+    with pytest.raises(TypeError):                    # no safe cast to complex128
+        permanent(np.ones((2, 2), dtype=np.clongdouble), [1, 1], [1, 1])
+
+
+def test_compute_without_a_device_fails_loudly(lib):
+    if lib.pq_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(_lib.PqPermError) as e:
+        permanent(haar(3, 1), [1, 1, 1], [1, 1, 1])
+    assert e.value.code == _lib.PQ_ERR_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+    with pytest.raises(_lib.PqPermError):
+        permanent_laplace(haar(3, 1), [1, 1, 0], [1, 1, 1])
+
+
+def test_finish_scaling():
+    from piquasso_b200.distributed import finish
+    v = finish([3.0, 0.5, -8.0, 0.0], 4)
+    assert v == complex(3.5 / 8, -1.0)
+
+
+def test_pybind_module_surface():
+    """Same module name, callables, keyword names and overload order as the
+    reference binding (piquasso/_math/permanent.cpp:71-85)."""
+    from piquasso_b200.native import permanent as native
+    assert native.__name__.endswith("permanent")
+    doc = native.permanent.__doc__
+    assert doc.index("numpy.complex64") < doc.index("numpy.complex128")
+    assert "matrix" in doc and "rows" in doc and "cols" in doc
+    z = np.zeros(3, int)
+    assert native.permanent(np.ones((3, 3), dtype=np.complex64), rows=z, cols=z).dtype == np.complex64
+    assert native.permanent(np.ones((3, 3)), rows=z, cols=z).dtype == np.complex128
+    assert native.permanent(np.ones((3, 3), dtype=np.int64), z, z).dtype == np.complex128
+    out = native.permanent_laplace(np.ones((0, 0), dtype=complex), [], [])
+    assert out.shape == (1,) and out[0] == 1
+    with pytest.raises(RuntimeError):
+        native.permanent(np.eye(2, dtype=complex), [1, 1], [1, 0])

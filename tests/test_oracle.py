@@ -1,0 +1,167 @@
+"""The oracle is pinned before it is trusted: the C restatement
+(oracle/perm_oracle.c) against the reference's own golden values, against
+outputs of the compiled reference (tests/golden/, made by make_golden.py),
+against the textbook definition and against the long-double arbiter."""
+
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden_complex, golden_matrix, haar, load_golden, relerr
+
+
+def test_reference_test_goldens():
+    """Every permanent() call the reference's tests/_math/test_permanent.py and
+    detection-probability tests make (inputs and compiled-reference outputs)."""
+    cases = load_golden("permanent_reference_tests.json")
+    assert len(cases) >= 10
+    for case in cases:
+        m = golden_matrix(case["matrix"])
+        want = golden_complex(case["value"])
+        got = oracle.permanent(m, case["rows"], case["cols"])
+        tol = 1e-5 if m.dtype == np.complex64 else 1e-12
+        assert abs(got - want) <= tol * max(1.0, abs(want)), case["source"]
+
+
+def test_reference_literal_goldens():
+    """Literal expected values typed in the reference tests
+    (tests/_math/test_permanent.py:24-30, 120-126; tests/jax_extensions/
+    test_permanent_unit.py:58-131)."""
+    assert np.isclose(oracle.permanent(np.array([[4.2]]), [1], [1]), 4.2)
+    u = np.array([[1, 1j], [1, -1j]]) / np.sqrt(2)
+    assert np.isclose(oracle.permanent(u, [2, 0], [0, 2]), -1)
+    assert np.isclose(oracle.permanent(np.zeros((0, 0)), [], []), 1.0)
+    assert np.isclose(oracle.permanent(np.array([[0.0]]), [1], [1]), 0.0)
+    assert np.isclose(oracle.permanent(np.array([[1, -2], [-3, 4]]), [1, 1], [1, 1]), 10.0)
+    assert np.isclose(oracle.permanent(np.full((3, 3), 1e10), [1, 1, 1], [1, 1, 1]), 6e30,
+                      rtol=1e-10)
+    assert np.isclose(oracle.permanent(np.array([[2, 3], [4, 5]]), [3, 0], [2, 1]), 72.0)
+    assert np.isclose(oracle.permanent(np.eye(8), np.ones(8, int), np.ones(8, int)), 1.0)
+    assert np.isclose(oracle.permanent(np.random.rand(4, 4), np.zeros(4, int), np.zeros(4, int)),
+                      1.0)
+    with pytest.raises(RuntimeError):
+        oracle.permanent(np.eye(2), [1, 1], [1, 0])
+
+
+def test_haar_goldens_from_compiled_reference():
+    for case in load_golden("permanent_haar.json"):
+        m = golden_matrix(case["matrix"])
+        want = golden_complex(case["value"])
+        got = oracle.permanent(m, case["rows"], case["cols"])
+        assert abs(got - want) <= 1e-11 * max(abs(want), 1e-3), case["source"]
+
+
+def test_laplace_goldens_from_compiled_reference():
+    cases = load_golden("laplace.json")
+    assert len(cases) > 100
+    for case in cases:
+        m = golden_matrix(case["matrix"])
+        want = np.array([golden_complex(z) for z in case["value"]])
+        got = oracle.permanent_laplace(m, case["rows"], case["cols"])
+        assert got.shape == want.shape, case["source"]
+        assert np.allclose(got, want, rtol=1e-11, atol=1e-14), case["source"]
+
+
+def test_gray_counter_matches_reference_traces():
+    """src/n_aryGrayCodeCounter.hpp initialize()/next() traces of the compiled
+    reference counter."""
+    for case in load_golden("gray.json"):
+        g0, trace = oracle.gray_trace(case["limits"], case["offset"], len(case["trace"]))
+        assert g0.tolist() == case["gray0"]
+        assert [list(t) for t in trace] == case["trace"]
+
+
+def test_gray_code_properties():
+    rng = np.random.default_rng(0)
+    for _ in range(30):
+        limits = rng.integers(1, 5, size=rng.integers(1, 6)).tolist()
+        total = int(np.prod(limits))
+        g0, trace = oracle.gray_trace(limits, 0, total)
+        assert len(trace) == total - 1
+        seen = {tuple(g0)}
+        g = list(g0)
+        for changed, prev, value in trace:
+            assert abs(prev - value) == 1 and g[changed] == prev
+            g[changed] = value
+            seen.add(tuple(g))
+        assert len(seen) == total  # every code exactly once
+
+
+def test_against_the_definition():
+    rng = np.random.default_rng(1)
+    for trial in range(25):
+        d = int(rng.integers(1, 5))
+        nph = int(rng.integers(1, 6))
+        rows = rng.multinomial(nph, np.ones(d) / d)
+        cols = rng.multinomial(nph, np.ones(d) / d)
+        a = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+        want = oracle.permanent_definition(a, rows, cols)
+        got = oracle.permanent(a, rows, cols)
+        assert abs(got - want) <= 1e-10 * max(1.0, abs(want))
+
+
+def test_laplace_is_the_minor_identity():
+    """permanent_laplace(A, rows, cols)[l] == permanent(A, rows, cols - e_l)
+    (the reference has no direct test of this entry)."""
+    rng = np.random.default_rng(2)
+    for trial in range(20):
+        d = int(rng.integers(2, 6))
+        k = int(rng.integers(2, 7))
+        rows = rng.multinomial(k - 1, np.ones(d) / d)
+        cols = rng.multinomial(k, np.ones(d) / d)
+        a = haar(d, trial)
+        lap = oracle.permanent_laplace(a, rows, cols)
+        for l in range(d):
+            if cols[l] == 0:
+                continue
+            c2 = cols.copy()
+            c2[l] -= 1
+            assert abs(lap[l] - oracle.permanent(a, rows, c2)) < 1e-11
+
+
+def test_long_double_arbiter_and_closed_forms():
+    """rank-1 A = u v^T has perm = n! prod(u) prod(v); all-ones J_n has n!."""
+    for n in (5, 9, 14):
+        rng = np.random.default_rng(n)
+        u = np.exp(2j * np.pi * rng.random(n))
+        v = np.exp(2j * np.pi * rng.random(n))
+        a = np.outer(u, v)
+        exact = math.factorial(n) * np.prod(u) * np.prod(v)
+        ones = np.ones(n, int)
+        assert relerr(oracle.permanent(a, ones, ones, precision=1), exact) < 1e-13
+        assert relerr(oracle.permanent(a, ones, ones), exact) < 1e-11
+        assert relerr(oracle.permanent(np.ones((n, n)), ones, ones, precision=1),
+                      math.factorial(n)) < 1e-14
+
+
+def test_job_count_does_not_change_the_sum():
+    """term(offset) is a pure function of the offset (src/permanent.cpp:158-164):
+    any job split sums the same multiset of terms."""
+    a = haar(9, 9)
+    ones = np.ones(9, int)
+    vals = [oracle.permanent(a, ones, ones, njobs=j) for j in (1, 3, 32, 256)]
+    for v in vals[1:]:
+        assert relerr(v, vals[0]) < 1e-12
+    whole, _, idx_max = oracle.partial(a, ones, ones, 0, 256)
+    assert idx_max == 256
+    halves = oracle.partial(a, ones, ones, 0, 100)[0] + oracle.partial(a, ones, ones, 100, 256)[0]
+    assert relerr(halves[0], whole[0]) < 1e-14
+    assert relerr(whole[0] / 2 ** 8, vals[0]) < 1e-12
+
+
+def test_compiled_reference_when_present():
+    """Where oracle/_ref exists (it travels to the GPU box) the restatement and
+    the unmodified reference agree to the last bits on fresh random inputs."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built and reference sources absent")
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        d = int(rng.integers(2, 8))
+        nph = int(rng.integers(1, 9))
+        rows = rng.multinomial(nph, np.ones(d) / d)
+        cols = rng.multinomial(nph, np.ones(d) / d)
+        a = haar(d, 300 + trial)
+        assert relerr(oracle.permanent(a, rows, cols), oracle.ref_permanent(a, rows, cols)) < 1e-12 \
+            or abs(oracle.ref_permanent(a, rows, cols)) < 1e-14
