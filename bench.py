@@ -10,15 +10,16 @@ For N > 1 the driver launches one rank per GPU with torchrun; run by hand with
 A "step" is one complete permanent of the 40x40 Haar-random unitary: its
 2^39-term Gray-code space is split over the N ranks (contiguous segment
 ranges), every rank walks its share with the sm_100a kernels, and ONE NCCL
-all-reduce of four doubles combines the partials (strong scaling: the total
+all-gather of four doubles per rank (summed error-free on every rank) combines
+the partials (strong scaling: the total
 work is fixed).  Rank 0 prints ONE JSON line.
 
 * ``value``   -- terms/s, device-timed (CUDA events on the launching stream
   around exactly K steps, max over ranks), inputs resident in HBM
-  (``pq_perm_job_*``), the all-reduce inside the timed region.
+  (``pq_perm_job_*``), the all-gather inside the timed region.
 * ``e2e``     -- the same K steps through the public host-buffer API
-  (``piquasso_b200.distributed.permanent_allreduce`` == ``permanent`` at N=1):
-  host planning, H2D of the matrix, kernels, all-reduce, D2H of the result,
+  (``piquasso_b200.distributed.permanent_allgather`` == ``permanent`` at N=1):
+  host planning, H2D of the matrix, kernels, all-gather, D2H of the result,
   wall clock, max over ranks.
 * ``roofline``-- FP64 pipe: algorithmic flops (8n+2 per term) of
   rank 0's walk kernel over its CUDA-event duration, against the DFMA
@@ -220,7 +221,7 @@ def main_arm(args):
     import torch.distributed as dist
 
     from piquasso_b200 import _lib
-    from piquasso_b200.distributed import finish, permanent_allreduce
+    from piquasso_b200.distributed import combine, finish, permanent_allgather
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -256,6 +257,7 @@ def main_arm(args):
     my_terms = lib.pq_perm_job_terms(job)
 
     partial = torch.zeros(4, dtype=torch.float64, device=dev)
+    gathered = torch.zeros(4 * world, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
 
@@ -264,7 +266,7 @@ def main_arm(args):
         _lib.check(lib.pq_perm_job_launch(job, ctypes.c_void_p(stream.cuda_stream),
                                           ctypes.c_void_p(partial.data_ptr())))
         if world > 1:
-            dist.all_reduce(partial, op=dist.ReduceOp.SUM)
+            dist.all_gather_into_tensor(gathered, partial)
 
     def barrier():
         if world > 1:
@@ -288,7 +290,7 @@ def main_arm(args):
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = lib.pq_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
-    result = finish(partial.cpu().numpy(), n)
+    result = finish(combine(gathered.cpu().numpy()) if world > 1 else partial.cpu().numpy(), n)
 
     hist = np.zeros(max(K, 1))
     nh = lib.pq_kernel_ms_history(local_rank, hist.ctypes.data_as(_lib.c_double_p), K)
@@ -306,11 +308,11 @@ def main_arm(args):
         launches_total = int(launches)
 
     # ---- end to end through the public host-buffer API ------------------------
-    permanent_allreduce(a, ones, ones, device_index=local_rank)  # one untimed call
+    permanent_allgather(a, ones, ones, device_index=local_rank)  # one untimed call
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        e2e_result = permanent_allreduce(a, ones, ones, device_index=local_rank)
+        e2e_result = permanent_allgather(a, ones, ones, device_index=local_rank)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -329,7 +331,7 @@ def main_arm(args):
         cfg = workload_config(n)
         cfg.update({
             "partition": "%d segments of %d terms, contiguous 1/%d share per rank; one NCCL "
-                         "all-reduce (sum, 4 x f64) per step" % (info.nseg, info.seg_len, world),
+                         "all-gather (4 x f64 per rank) + error-free sum per step" % (info.nseg, info.seg_len, world),
             "kernel": {1: "generic n-ary walk", 2: "binary constant-bank walk"}[info.kernel],
             "l2": "256 MiB memset between steps (inside the timed region; the path's working "
                   "set is the %d-byte matrix, not HBM-resident data)" % (h2d // world),

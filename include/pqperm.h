@@ -47,7 +47,7 @@ int pq_device_count(void);
 /* Devices used by the host-buffer entry points below; default = device 0 only.
  * With n > 1 a single permanent's term space is split over the devices and
  * the partial sums are combined (single process; the multi-process path is
- * pq_perm_partial_c128 + an NCCL all-reduce done by the caller). */
+ * pq_perm_partial_c128 + an NCCL all-gather done by the caller). */
 int pq_set_devices(const int *device_ids, int n);
 
 /* ---------------------------------------------------------------------
@@ -100,8 +100,9 @@ int pq_perm_laplace_batch_c128(int nprob, const double *A, const int64_t *a_off,
  * The UNSCALED partial sum is left in DEVICE memory as four doubles
  * (re_hi, re_lo, im_hi, im_lo; value = hi + lo) at d_partial on `device`,
  * enqueued on `stream` (a cudaStream_t, NULL = the library's own stream,
- * synchronised before returning).  The caller sums the four doubles over
- * ranks (one NCCL all-reduce) and calls pq_perm_finish.
+ * synchronised before returning).  The caller gathers the four doubles of
+ * every rank (one NCCL all-gather), sums them with pq_perm_combine and calls
+ * pq_perm_finish.
  *
  * *status (host int, may be NULL) receives 0 when a partial was enqueued or
  * 1 when the problem is one of the reference's trivial cases and `trivial`
@@ -111,6 +112,12 @@ int pq_perm_partial_c128(const double *A, int R, int C, const int32_t *rows,
                          const int32_t *cols, int part, int nparts, int device,
                          void *stream, double *d_partial, int *status,
                          double trivial[2]);
+
+/* Error-free sum of n partial quadruples (re_hi, re_lo, im_hi, im_lo) into
+ * one, in index order.  Rank partials can be orders of magnitude larger than
+ * their sum, so they must not be added component-wise in plain doubles: gather
+ * them (one NCCL all-gather of 4 doubles per rank) and combine here. */
+int pq_perm_combine(const double *quads, int n, double out4[4]);
 
 /* hi/lo quadruple + sum(rows) -> permanent: (hi+lo) * 2^-(sum_rows-1)
  * (src/permanent.cpp:259). */

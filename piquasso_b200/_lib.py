@@ -75,6 +75,7 @@ SIGNATURES = [
     ("pq_perm_job_terms", ctypes.c_int64, [ctypes.c_void_p]),
     ("pq_perm_job_destroy", ctypes.c_int, [ctypes.c_void_p]),
     ("pq_kernel_ms_history", ctypes.c_int, [ctypes.c_int, c_double_p, ctypes.c_int]),
+    ("pq_perm_combine", ctypes.c_int, [c_double_p, ctypes.c_int, c_double_p]),
     ("pq_perm_finish", ctypes.c_int, [c_double_p, ctypes.c_int, c_double_p]),
     ("pq_perm_plan", ctypes.c_int,
      [ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, ctypes.POINTER(PlanInfo)]),

@@ -22,25 +22,24 @@ namespace pqperm {
 
 // parts of the binary kernel family (pqperm_kernels_binary.cu)
 #define PQ_DECL_PART(k)                                                                 \
-    cudaError_t launch_binary_part_##k(int, int, int, const WalkParams &, const double2 *, \
-                                       cudaMemcpyKind, int, int, cudaStream_t, LaunchInfo *);
+    cudaError_t launch_binary_part_##k(int, int, const WalkParams &, const double2 *, int,  \
+                                       int, cudaStream_t, LaunchInfo *);
 PQ_DECL_PART(0)
 PQ_DECL_PART(1)
 PQ_DECL_PART(2)
 PQ_DECL_PART(3)
 #undef PQ_DECL_PART
 
-cudaError_t launch_binary(int nc, int B, int chains, const WalkParams &P,
-                          const double2 *A2_src, cudaMemcpyKind kind, int num_sms,
-                          int max_grid, cudaStream_t stream, LaunchInfo *info)
+cudaError_t launch_binary(int nc, int B, const WalkParams &P, const double2 *d_A2,
+                          int num_sms, int max_grid, cudaStream_t stream, LaunchInfo *info)
 {
     if (nc <= 20)
-        return launch_binary_part_0(nc, B, chains, P, A2_src, kind, num_sms, max_grid, stream, info);
+        return launch_binary_part_0(nc, B, P, d_A2, num_sms, max_grid, stream, info);
     if (nc <= 30)
-        return launch_binary_part_1(nc, B, chains, P, A2_src, kind, num_sms, max_grid, stream, info);
+        return launch_binary_part_1(nc, B, P, d_A2, num_sms, max_grid, stream, info);
     if (nc <= 40)
-        return launch_binary_part_2(nc, B, chains, P, A2_src, kind, num_sms, max_grid, stream, info);
-    return launch_binary_part_3(nc, B, chains, P, A2_src, kind, num_sms, max_grid, stream, info);
+        return launch_binary_part_2(nc, B, P, d_A2, num_sms, max_grid, stream, info);
+    return launch_binary_part_3(nc, B, P, d_A2, num_sms, max_grid, stream, info);
 }
 
 } // namespace pqperm
@@ -235,9 +234,8 @@ static int launch_plan(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64_
     const int slot = (int)(c->ring_next % kTimingRing);
     PQ_CUDA(cudaEventRecord(c->ring0[slot], stream));
     if (plan.kernel == 2) {
-        e = launch_binary(plan.NC, plan.B, plan.chains, P,
-                          reinterpret_cast<const double2 *>(c->d_A2),
-                          cudaMemcpyDeviceToDevice, c->num_sms, kMaxGrid, stream, &info);
+        e = launch_binary(plan.NC, plan.B, P, reinterpret_cast<const double2 *>(c->d_A2),
+                          c->num_sms, kMaxGrid, stream, &info);
     } else {
         e = launch_generic(plan.NCP, fast, fast, P, c->num_sms, kMaxGrid, stream, &info);
     }
@@ -327,6 +325,34 @@ extern "C" double pq_last_kernel_ms(int device)
     if (device < 0 || device >= (int)g_ctx.size() || !g_ctx[device])
         return -1.0;
     return g_ctx[device]->last_kernel_ms;
+}
+
+// Error-free accumulation of (hi, lo) pairs on the host: the rank partials can
+// be orders of magnitude larger than their sum, so a plain sum of the hi parts
+// would throw away what the double-double kernels preserved.
+static void dd_acc_host(double &hi, double &lo, double bhi, double blo)
+{
+    const double s = hi + bhi;
+    const double bb = s - hi;
+    const double e = (hi - (s - bb)) + (bhi - bb);
+    hi = s;
+    lo += e + blo;
+}
+
+extern "C" int pq_perm_combine(const double *quads, int n, double out4[4])
+{
+    if (!quads || !out4 || n < 0)
+        return fail(PQ_ERR_BAD_ARG, "null pointer");
+    double rh = 0.0, rl = 0.0, ih = 0.0, il = 0.0;
+    for (int i = 0; i < n; i++) { // fixed order => reproducible
+        dd_acc_host(rh, rl, quads[4 * i + 0], quads[4 * i + 1]);
+        dd_acc_host(ih, il, quads[4 * i + 2], quads[4 * i + 3]);
+    }
+    out4[0] = rh;
+    out4[1] = rl;
+    out4[2] = ih;
+    out4[3] = il;
+    return PQ_OK;
 }
 
 extern "C" int pq_perm_finish(const double partial[4], int sum_rows, double out[2])
@@ -437,7 +463,7 @@ static int perm_run(const double *A, int R, int C, const int32_t *rows, const in
             return fail(rc, err);
     }
     // small problems are not worth a second device
-    const int used = (ndev > 1 && plan.nseg >= (int64_t)ndev * 4096) ? ndev : 1;
+    const int used = (ndev > 1 && plan.nseg >= (int64_t)ndev * 4096) ? std::min(ndev, 64) : 1;
     for (int i = 0; i < used; i++) {
         DeviceCtx *c = ctx[i];
         PQ_CUDA(cudaSetDevice(c->device));
@@ -451,7 +477,7 @@ static int perm_run(const double *A, int R, int C, const int32_t *rows, const in
         PQ_CUDA(cudaMemcpyAsync(c->h_pinned + kA2Doubles, c->d_out, 4 * sizeof(double),
                                 cudaMemcpyDeviceToHost, c->stream));
     }
-    double tot[4] = {0.0, 0.0, 0.0, 0.0};
+    double quads[4 * 64];
     for (int i = 0; i < used; i++) {
         DeviceCtx *c = ctx[i];
         PQ_CUDA(cudaSetDevice(c->device));
@@ -459,10 +485,11 @@ static int perm_run(const double *A, int R, int C, const int32_t *rows, const in
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
             c->last_kernel_ms = ms;
-        // fixed device order => reproducible; hi and lo parts are summed separately
         for (int k = 0; k < 4; k++)
-            tot[k] += c->h_pinned[kA2Doubles + k];
+            quads[4 * i + k] = c->h_pinned[kA2Doubles + k];
     }
+    double tot[4];
+    pq_perm_combine(quads, used, tot); // fixed device order, error-free
     return pq_perm_finish(tot, plan.sum_rows, out);
 }
 
@@ -571,6 +598,7 @@ extern "C" int pq_perm_segment_sums_c128(const double *A, int R, int C, const in
         return fail(PQ_ERR_BAD_ARG, "segment range outside the plan");
     double *d_seg = nullptr;
     PQ_CUDA(cudaMalloc(&d_seg, (size_t)nseg * 2 * sizeof(double)));
+    PQ_CUDA(cudaMemsetAsync(d_seg, 0, (size_t)nseg * 2 * sizeof(double), c->stream));
     rc = enqueue_walk(plan, c, seg_begin, seg_begin + nseg, c->d_out, d_seg, c->stream);
     if (rc == PQ_OK) {
         cudaError_t e = cudaMemcpyAsync(out, d_seg, (size_t)nseg * 2 * sizeof(double),

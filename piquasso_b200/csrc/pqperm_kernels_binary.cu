@@ -1,8 +1,8 @@
-// pqperm_kernels_binary.cu -- instantiations of the binary constant-bank walk
-// for column counts PQ_BIN_LO..PQ_BIN_HI.  Compiled once per range
+// pqperm_kernels_binary.cu -- instantiations of the binary hypercube walk
+// (kernel 2) for column counts PQ_BIN_LO..PQ_BIN_HI.  Compiled once per range
 // (-DPQ_BIN_PART=k -DPQ_BIN_LO=a -DPQ_BIN_HI=b) so the ranges build in
-// parallel; each part owns its own __constant__ copy of the matrix (separate
-// cubins, no relocatable device code).
+// parallel; each part owns its own __constant__ copies (separate cubins, no
+// relocatable device code).
 #include "pqperm_device.cuh"
 
 #ifndef PQ_BIN_PART
@@ -10,9 +10,10 @@
 #endif
 
 namespace pqperm {
-// (D+1) x NC doubled matrix of the permanent being computed; rows 1..B are
-// addressed with compile-time offsets inside the unrolled inner block, the
-// rest with a warp-uniform run-time row index (LDCU, uniform datapath).
+// (D+1) x NC doubled matrix of the permanent being computed: rows 1..B with
+// compile-time offsets inside the unrolled column loop, the others with a
+// warp-uniform run-time row index (block-level Gray moves, seeding); both
+// through the uniform datapath (LDCU).
 __constant__ double2 c_matrix[(kBinMaxCols + 1) * kBinMaxCols];
 } // namespace pqperm
 #define PQ_BINARY_CONST_MATRIX ::pqperm::c_matrix
@@ -25,52 +26,50 @@ __constant__ double2 c_matrix[(kBinMaxCols + 1) * kBinMaxCols];
 namespace pqperm {
 
 template <int NC>
-static cudaError_t launch_binary_nc(int B, int chains, const WalkParams &P, int num_sms, int max_grid,
+static cudaError_t launch_binary_nc(int B, const WalkParams &P, int num_sms, int max_grid,
                                     cudaStream_t stream, LaunchInfo *info)
 {
-    // 64-thread CTAs: at ~4*NC+40 registers per thread the register file holds
-    // only a few warps per SM, and small CTAs waste the fewest of them.
+    // 64-thread CTAs: at ~4*NC + 4*2^B registers per thread the register file
+    // holds only a few warps per SM, and small CTAs waste the fewest of them.
     constexpr int NT = 64;
-#define PQ_VARIANT(BB, CC)                                                              \
-    if (B == BB && chains == CC)                                                        \
-        return launch_walk(perm_walk_binary<NC, BB, CC, NT>, P, P, NT, 0, num_sms,      \
-                           max_grid, stream, info);
-    PQ_VARIANT(1, 2)
-    PQ_VARIANT(2, 1)
-    PQ_VARIANT(2, 2)
-    PQ_VARIANT(3, 1)
-    PQ_VARIANT(3, 2)
+#define PQ_VARIANT(BB)                                                                  \
+    if (B == BB)                                                                        \
+        return launch_walk(perm_walk_binary<NC, BB, NT>, P, P, NT, 0, num_sms, max_grid,    \
+                           stream, info);
+    PQ_VARIANT(2)
+    PQ_VARIANT(3)
+    if constexpr (NC <= 32) {
+        PQ_VARIANT(4)
+    }
 #undef PQ_VARIANT
     return cudaErrorInvalidValue;
 }
 
 template <int NC, int HI>
-static cudaError_t dispatch_binary(int nc, int B, int chains, const WalkParams &P, int num_sms,
+static cudaError_t dispatch_binary(int nc, int B, const WalkParams &P, int num_sms,
                                    int max_grid, cudaStream_t stream, LaunchInfo *info)
 {
     if (nc == NC)
-        return launch_binary_nc<NC>(B, chains, P, num_sms, max_grid, stream, info);
+        return launch_binary_nc<NC>(B, P, num_sms, max_grid, stream, info);
     if constexpr (NC < HI)
-        return dispatch_binary<NC + 1, HI>(nc, B, chains, P, num_sms, max_grid, stream, info);
+        return dispatch_binary<NC + 1, HI>(nc, B, P, num_sms, max_grid, stream, info);
     else
         return cudaErrorInvalidValue;
 }
 
-cudaError_t PQ_CONCAT(launch_binary_part_, PQ_BIN_PART)(int nc, int B, int chains,
-                                                        const WalkParams &P,
-                                                        const double2 *A2_src,
-                                                        cudaMemcpyKind kind, int num_sms,
+cudaError_t PQ_CONCAT(launch_binary_part_, PQ_BIN_PART)(int nc, int B, const WalkParams &P,
+                                                        const double2 *d_A2, int num_sms,
                                                         int max_grid, cudaStream_t stream,
                                                         LaunchInfo *info)
 {
     if (nc < PQ_BIN_LO || nc > PQ_BIN_HI)
         return cudaErrorInvalidValue;
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_matrix, A2_src,
-                                            (size_t)(P.D + 1) * nc * sizeof(double2), 0, kind,
-                                            stream);
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_matrix, d_A2,
+                                            (size_t)(P.D + 1) * nc * sizeof(double2), 0,
+                                            cudaMemcpyDeviceToDevice, stream);
     if (e != cudaSuccess)
         return e;
-    return dispatch_binary<PQ_BIN_LO, PQ_BIN_HI>(nc, B, chains, P, num_sms, max_grid, stream, info);
+    return dispatch_binary<PQ_BIN_LO, PQ_BIN_HI>(nc, B, P, num_sms, max_grid, stream, info);
 }
 
 } // namespace pqperm

@@ -18,20 +18,15 @@ struct LaunchInfo {
 // Width the generic kernel is instantiated for: smallest multiple of 4 >= nc.
 inline int generic_padded_cols(int nc) { return nc <= 4 ? 4 : (nc + 3) / 4 * 4; }
 
-// Can the binary constant-bank kernel take this width / unroll?
-bool binary_kernel_available(int nc, int B, int chains);
-
 // Launch the generic walk for P (P.partials must hold max_grid * 4 doubles).
 cudaError_t launch_generic(int ncp, bool binary, bool unitcols, const WalkParams &P,
                            int num_sms, int max_grid, cudaStream_t stream,
                            LaunchInfo *info);
 
-// Binary constant-bank walk.  `A2_src` ((P.D+1) x nc double2, host-pinned or
-// device) is copied into the kernel's __constant__ matrix on `stream` first.
-cudaError_t launch_binary(int nc, int B, int chains, const WalkParams &P,
-                          const double2 *A2_src,
-                          cudaMemcpyKind kind, int num_sms, int max_grid,
-                          cudaStream_t stream, LaunchInfo *info);
+// Binary hypercube walk (kernel 2).  `d_A2` ((P.D+1) x nc double2, device
+// memory) is copied into the kernel's __constant__ matrix on `stream` first.
+cudaError_t launch_binary(int nc, int B, const WalkParams &P, const double2 *d_A2,
+                          int num_sms, int max_grid, cudaStream_t stream, LaunchInfo *info);
 
 // out4[k] (+)= sum over n partial quadruples (double-double), one block.
 cudaError_t launch_reduce_partials(const double *partials, int n, double *out4,

@@ -11,8 +11,11 @@ constexpr int kMaxLowDigits = 24;       // digits walked inside one segment
 constexpr int kMaxMultiplicity = 254;   // radix r+1 is stored in a byte
 constexpr int kBinMinCols = 8;          // narrowest binary constant-bank kernel
 constexpr int kBinMaxCols = 48;         // widest binary constant-bank kernel
-constexpr int kBinDefaultUnroll = 2;    // log2 of the unrolled inner block
-constexpr int kBinDefaultChains = 2;    // independent product chains
+constexpr int kBinMaxBlockExp = 4;      // kernel 2: at most 2^4 terms per block
+// kernel 2: log2 of the terms per block for nc columns (register budget:
+// 4*nc for the row sums + 4 * 2^B for the running products)
+inline int binary_block_exponent(int /*nc*/) { return 3; }  // measured best for 20 <= nc <= 48
+constexpr int kBinMinDigitsAuto = 25;   // below 2^25 terms the generic walk's lower setup cost wins
 constexpr int64_t kMaxSegLenBinary = INT64_C(1) << 14;
 constexpr int64_t kMaxSegLenNary = INT64_C(1) << 12;
 

@@ -129,9 +129,8 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
 
     // ---- kernel choice ------------------------------------------------------
     int choice = opt.kernel_choice;
-    int forced_B = 0, forced_chains = 0;
+    int forced_B = 0;
     if (choice >= 10) {
-        forced_chains = choice / 100;
         forced_B = (choice / 10) % 10;
         choice = choice % 10;
     }
@@ -139,10 +138,10 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
                         plan.NC >= kBinMinCols && plan.NC <= kBinMaxCols;
     plan.kernel = 1;
     if (bin_ok && choice != 1) {
-        plan.B = forced_B ? forced_B : kBinDefaultUnroll;
-        plan.chains = forced_chains ? forced_chains : kBinDefaultChains;
-        // the binary kernel needs at least one unrolled block per segment
-        if (plan.D >= plan.B + (choice == 2 ? 0 : 4))
+        plan.B = forced_B ? forced_B : binary_block_exponent(plan.NC);
+        // automatic choice: only where the term space is large enough to repay the
+        // constant-bank upload; forced (tests, tuning): wherever a block fits
+        if (plan.D >= (choice == 2 ? plan.B : kBinMinDigitsAuto))
             plan.kernel = 2;
     }
     plan.NCP = plan.kernel == 2 ? plan.NC : (plan.NC <= 4 ? 4 : (plan.NC + 3) / 4 * 4);

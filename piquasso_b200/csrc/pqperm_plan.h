@@ -43,8 +43,7 @@ struct Plan {
     int64_t W = 1;            // terms per segment
     int64_t nseg = 1;         // segments
     int kernel = 1;           // 1 generic, 2 binary constant-bank
-    int B = 0;                // unroll exponent of kernel 2
-    int chains = 0;           // product chains of kernel 2
+    int B = 0;                // kernel 2: 2^B terms (one hypercube of the low digits) per block
     std::vector<uint8_t> sched;     // [W]   (generic, non-binary)
     std::vector<double> wtab;       // [W]
     std::vector<double> binom;      // flattened C(r_d, g)
@@ -52,7 +51,7 @@ struct Plan {
 };
 
 struct PlanOptions {
-    int kernel_choice = 0;    // 0 auto, 1 generic, 2 binary; 2 + 10*B + 100*chains forces a variant
+    int kernel_choice = 0;    // 0 auto, 1 generic, 2 binary; 2 + 10*B forces the block exponent
     int64_t seg_len_hint = 0; // 0 auto
     int num_sms = 148;
     bool laplace = false;     // plan for the Laplace walk (different per-term cost)

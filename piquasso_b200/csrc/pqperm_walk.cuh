@@ -145,12 +145,13 @@ __device__ __forceinline__ void column_product(const WalkParams &P, const double
             for (int j = j0 + 1; j < j1; j++)
                 cmul(cr[c], ci[c], sr[j], si[j]);
         }
-        if (CH == 4) {
-            cmul(cr[0], ci[0], cr[1], ci[1]);
-            cmul(cr[2], ci[2], cr[3], ci[3]);
-            cmul(cr[0], ci[0], cr[2], ci[2]);
-        } else if (CH == 2) {
-            cmul(cr[0], ci[0], cr[1], ci[1]);
+        // pairwise combination of the partial chains (no extra multiplies:
+        // (NC - CH) + (CH - 1) = NC - 1 complex products whatever CH is)
+#pragma unroll
+        for (int stride = 1; stride < CH; stride *= 2) {
+#pragma unroll
+            for (int c = 0; c + stride < CH; c += 2 * stride)
+                cmul(cr[c], ci[c], cr[c + stride], ci[c + stride]);
         }
         pr = cr[0];
         pi = ci[0];
@@ -255,18 +256,48 @@ __global__ void __launch_bounds__(NT) perm_walk_generic(const __grid_constant__ 
 }
 
 #ifdef PQ_BINARY_CONST_MATRIX
-// ---- kernel 2: binary constant-bank walk -----------------------------------
-// All multiplicities 1 (radix 2 everywhere): the step sequence inside an
-// aligned block of 2^B offsets is the ruler sequence, known at compile time.
-// The rows of digits 0..B-1 live in the kernel parameter block (constant
-// bank), so the 2^B - 1 inner steps are pure FP64: per column 2 DFMA with an
-// immediate-offset constant operand + 2 DMUL + 2 DFMA, no loads and no integer
-// bookkeeping.  Only the last step of each block moves a run-time digit
-// (B + ctz(block index + 1)) whose row comes from shared memory.
-template <int NC, int B, int CHAINS, int NT>
+#ifndef PQ_COL_CHUNK
+#define PQ_COL_CHUNK 8
+#endif
+
+// Scheduling fence: the unrolled column loop is one huge basic block and ptxas
+// tends to hoist the operand loads of all columns to its top.  Routing the
+// running products and the row pointer through an empty volatile asm keeps a
+// window of PQ_COL_CHUNK columns in flight.
+template <int NP>
+__device__ __forceinline__ void sched_fence(double (&pr)[NP], double (&pi)[NP],
+                                            const double2 *&ptr)
+{
+#pragma unroll
+    for (int t = 0; t < NP; t++)
+        asm volatile("" : "+d"(pr[t]), "+d"(pi[t]));
+    asm volatile("" : "+l"(ptr));
+}
+
+// ---- kernel 2: binary walk, one hypercube of the low digits per block ---------
+// All multiplicities 1 (radix 2 everywhere).  The 2^B offsets of an aligned
+// block share the Gray digits >= B and run through ALL 2^B values of the digits
+// 0..B-1 -- a hypercube whose corner (all low digits 0) is a per-thread vector
+// c_j and whose other vertices are c_j - sum_{d in e} 2 a_dj.  The term sign is
+// (-1)^{sum of the Gray digits >= B} * (-1)^{|e|}.
+//
+// A block is evaluated column-major: for column j the 2^B - 1 other vertices
+// are one add each (a binary tree of depth B from the corner; the B row
+// operands come from the constant bank through the uniform datapath,
+// LDCU.128 -> DADD R, R, -UR) and are multiplied straight into 2^B independent
+// running products, one per term; the same pass applies the block-level Gray
+// move (digit B + ctz(block+1), warp-uniform row) to the corner.  Per column
+// and block that is B + 1 operand fetches for 2^B terms, the products give the
+// FP64 pipe 2^B-way ILP with two warps per SM sub-partition resident, and
+// there is no per-step integer bookkeeping at all.
+// FP64 instructions per term: 2C (vertex adds + corner move) + 4(C-1)
+// (products) + 2 (signed sum)  =  6C - 2, as in the reference's hot loop
+// (src/permanent.cpp:218-250) but with every operand warp-uniform.
+template <int NC, int B, int NT>
 __global__ void __launch_bounds__(NT) perm_walk_binary(const __grid_constant__ WalkParams P)
 {
-    const double2 *smA = PQ_BINARY_CONST_MATRIX;
+    constexpr int NP = 1 << B;
+    const double2 *cA = PQ_BINARY_CONST_MATRIX;
 
     dd totre{0.0, 0.0}, totim{0.0, 0.0};
     const int nblk = (int)(P.W >> B);
@@ -276,82 +307,122 @@ __global__ void __launch_bounds__(NT) perm_walk_binary(const __grid_constant__ W
             break;
         if (seg >= P.seg_end)
             continue;
-        double sr[NC], si[NC];
-        unsigned dirmask;
-        double factor;
-        seed_segment<NC, true>(P, smA, seg, sr, si, dirmask, factor);
 
-        // direction of the next move of digits 0..B-1 as +-1.0
-        double sg[B];
+        // ---- corner of the segment's first block (cf. seed_segment): digits
+        // >= q from the segment index, digits B..q-1 at counter 0, digits < B at 0
+        double cr[NC], ci[NC];
 #pragma unroll
-        for (int d = 0; d < B; d++)
-            sg[d] = ((dirmask >> d) & 1u) ? 1.0 : -1.0;
-
-        dd segre{0.0, 0.0}, segim{0.0, 0.0};
-        double accr, acci;
-        column_product<NC, true, CHAINS>(P, sr, si, accr, acci); // term m = 0
-
-        for (int blk = 0; blk < nblk; ++blk) {
-#pragma unroll
-            for (int i = 1; i < (1 << B); ++i) {
-                // digit ctz(i): compile-time after unrolling
-                const int p = (i & 1) ? 0 : ((i & 2) ? 1 : ((i & 4) ? 2 : 3));
-#pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    const double2 a = smA[(p + 1) * NC + j];
-                    sr[j] = __fma_rn(sg[p], a.x, sr[j]);
-                    si[j] = __fma_rn(sg[p], a.y, si[j]);
-                }
-#pragma unroll
-                for (int d = 0; d < B; d++)
-                    if (d < p)
-                        sg[d] = -sg[d];
-                double pr, pi;
-                column_product<NC, true, CHAINS>(P, sr, si, pr, pi);
-                if (i & 1) {
-                    accr -= pr;
-                    acci -= pi;
-                } else {
-                    accr += pr;
-                    acci += pi;
-                }
+        for (int j = 0; j < NC; j++) {
+            const double2 a = cA[j];
+            cr[j] = a.x;
+            ci[j] = a.y;
+        }
+        const unsigned long long gh = (unsigned long long)seg ^ ((unsigned long long)seg >> 1);
+        int odd = __popcll(gh) & 1;
+        unsigned dirmask = 0;
+        for (int d = P.D - 1; d >= 0; --d) {
+            double w;
+            if (d >= P.q) {
+                w = ((gh >> (d - P.q)) & 1ull) ? -0.5 : 0.5; // rows are stored doubled
+            } else if (d >= B) {
+                dirmask |= (unsigned)odd << d;
+                w = odd ? -0.5 : 0.5;
+                odd = 0;
+            } else {
+                w = 0.5;
             }
-            if (blk + 1 < nblk) {
+            const double2 *row = cA + (d + 1) * NC;
+#pragma unroll
+            for (int j = 0; j < NC; j++) {
+                const double2 a = row[j];
+                cr[j] = __fma_rn(w, a.x, cr[j]);
+                ci[j] = __fma_rn(w, a.y, ci[j]);
+            }
+        }
+        const double factor = odd ? -1.0 : 1.0; // (-1)^{sum of the Gray digits >= B}
+
+        // blocks are summed in plain FP64 in groups of 8 and the group sums folded
+        // into the thread's double-double total
+        for (int blk0 = 0; blk0 < nblk; blk0 += 8) {
+            double accr = 0.0, acci = 0.0;
+            const int blk1 = min(nblk, blk0 + 8);
+            for (int blk = blk0; blk < blk1; ++blk) {
+                // the Gray move that leads from this block to the next one
+                const bool more = blk + 1 < nblk;
                 const int p = B + __ffs(blk + 1) - 1;
-                const double sgh = ((dirmask >> p) & 1u) ? 1.0 : -1.0;
+                const double sgh = more ? (((dirmask >> p) & 1u) ? 1.0 : -1.0) : 0.0;
                 dirmask ^= (1u << p) - 1u;
-#pragma unroll
-                for (int d = 0; d < B; d++)
-                    sg[d] = -sg[d];
-                const double2 *row = smA + (p + 1) * NC;
+                const double2 *rowh = cA + (more ? (p + 1) * NC : 0);
+
+                double pr[NP], pi[NP];
 #pragma unroll
                 for (int j = 0; j < NC; j++) {
-                    const double2 a = row[j];
-                    sr[j] = __fma_rn(sgh, a.x, sr[j]);
-                    si[j] = __fma_rn(sgh, a.y, si[j]);
+                    const double c0r = cr[j], c0i = ci[j];
+                    if (j == 0) {
+                        pr[0] = c0r;
+                        pi[0] = c0i;
+                    } else {
+                        cmul(pr[0], pi[0], c0r, c0i);
+                    }
+                    // vertex e = vertex (e with its lowest set bit cleared) minus the
+                    // doubled row of that bit: one add per vertex, every operand an
+                    // exact matrix entry (a table of pre-rounded subset sums would put
+                    // the SAME rounding error into one vertex of every block, which
+                    // the cancellation of the Glynn sum amplifies)
+                    double vr[NP], vi[NP];
+                    vr[0] = c0r;
+                    vi[0] = c0i;
+#pragma unroll
+                    for (int e = 1; e < NP; e++) {
+                        const int d = (e & 1) ? 0 : ((e & 2) ? 1 : ((e & 4) ? 2 : 3));
+                        const double2 a = cA[(d + 1) * NC + j];
+                        vr[e] = vr[e & (e - 1)] - a.x;
+                        vi[e] = vi[e & (e - 1)] - a.y;
+                        if (j == 0) {
+                            pr[e] = vr[e];
+                            pi[e] = vi[e];
+                        } else {
+                            cmul(pr[e], pi[e], vr[e], vi[e]);
+                        }
+                    }
+                    const double2 ah = rowh[j];
+                    cr[j] = __fma_rn(sgh, ah.x, c0r);
+                    ci[j] = __fma_rn(sgh, ah.y, c0i);
+                    if (PQ_COL_CHUNK > 0 && (j % (PQ_COL_CHUNK > 0 ? PQ_COL_CHUNK : 1)) ==
+                            PQ_COL_CHUNK - 1 && j + 1 < NC)
+                        sched_fence<NP>(pr, pi, rowh);
                 }
-                double pr, pi;
-                column_product<NC, true, CHAINS>(P, sr, si, pr, pi);
-                dd_add(segre, accr);
-                dd_add(segim, acci);
-                accr = pr;
-                acci = pi;
+                // signed sum over the vertices: (-1)^{|e|}
+                double br = 0.0, bi = 0.0;
+#pragma unroll
+                for (int e = 0; e < NP; e++) {
+                    if (__builtin_popcount(e) & 1) {
+                        br -= pr[e];
+                        bi -= pi[e];
+                    } else {
+                        br += pr[e];
+                        bi += pi[e];
+                    }
+                }
+                // every block move flips one Gray digit >= B
+                if (blk & 1) {
+                    accr -= br;
+                    acci -= bi;
+                } else {
+                    accr += br;
+                    acci += bi;
+                }
+            }
+            dd_add(totre, factor * accr);
+            dd_add(totim, factor * acci);
+            if (P.segsums) {
+                P.segsums[2 * (seg - P.seg_begin)] += factor * accr;
+                P.segsums[2 * (seg - P.seg_begin) + 1] += factor * acci;
             }
         }
-        dd_add(segre, accr);
-        dd_add(segim, acci);
-        segre = dd_scale(segre, factor);
-        segim = dd_scale(segim, factor);
-        if (P.segsums) {
-            P.segsums[2 * (seg - P.seg_begin)] = segre.hi + segre.lo;
-            P.segsums[2 * (seg - P.seg_begin) + 1] = segim.hi + segim.lo;
-        }
-        dd_add(totre, segre);
-        dd_add(totim, segim);
     }
     block_reduce_store<NT>(totre, totim, P.partials + 4 * (size_t)blockIdx.x);
 }
-
 #endif // PQ_BINARY_CONST_MATRIX
 
 } // namespace pqperm

@@ -4,11 +4,15 @@ The Gray-code term space is cut into equal segments (``plan.plan``); rank g of
 G walks the contiguous segment range ``plan.segment_range(nseg, g, G)`` with
 the same kernels as the single-GPU call and leaves an UNSCALED double-double
 partial (re_hi, re_lo, im_hi, im_lo) in its own HBM.  The only exchange step
-of the path is ONE all-reduce (sum) of those four doubles -- NCCL over
+of the path is ONE collective on those four doubles -- NCCL over
 NVLink/NVSwitch when the process group is NCCL -- after which every rank holds
-the permanent.  The payload is 32 bytes: the collective is latency-bound, there
-is nothing to overlap, and the reference has no counterpart (its parallelism
-is one OpenMP loop, src/permanent.cpp:152-155).
+the permanent.  It is an all-GATHER followed by a local error-free sum
+(``pq_perm_combine``), not an all-reduce: the rank partials can be orders of
+magnitude larger than their sum, and a plain floating-point reduction of the
+hi parts would discard the low-order bits the kernels preserved.  The payload
+is 32 bytes per rank: the collective is latency-bound, there is nothing to
+overlap, and the reference has no counterpart (its parallelism is one OpenMP
+loop, src/permanent.cpp:152-155).
 """
 
 from __future__ import annotations
@@ -43,6 +47,16 @@ def _device_partial(a, r, c, part, nparts, device_index):
     return out
 
 
+def combine(quads):
+    """Error-free sum of per-rank quadruples, shape (G, 4) -> (4,)."""
+    lib = _lib.load()
+    q = np.ascontiguousarray(np.asarray(quads, dtype=np.float64)).reshape(-1, 4)
+    out = np.zeros(4)
+    _lib.check(lib.pq_perm_combine(q.ctypes.data_as(_lib.c_double_p), q.shape[0],
+                                   out.ctypes.data_as(_lib.c_double_p)))
+    return out
+
+
 def finish(partial4, sum_rows):
     """(hi+lo) * 2^-(sum_rows-1), src/permanent.cpp:259."""
     lib = _lib.load()
@@ -53,7 +67,7 @@ def finish(partial4, sum_rows):
     return complex(out[0], out[1])
 
 
-def permanent_allreduce(matrix, rows, cols, group=None, device_index=None):
+def permanent_allgather(matrix, rows, cols, group=None, device_index=None):
     """``permanent(matrix, rows, cols)`` computed by every rank of ``group``
     together; all ranks return the same 0-d complex128 array.
 
@@ -75,5 +89,13 @@ def permanent_allreduce(matrix, rows, cols, group=None, device_index=None):
     if isinstance(part, complex):
         return np.array(np.complex128(part))
     if world > 1:
-        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
-    return np.array(np.complex128(finish(part.cpu().numpy(), int(r.sum()))))
+        gathered = torch.empty(world * 4, dtype=part.dtype, device=part.device)
+        dist.all_gather_into_tensor(gathered, part, group=group)
+        total = combine(gathered.cpu().numpy())
+    else:
+        total = part.cpu().numpy()
+    return np.array(np.complex128(finish(total, int(r.sum()))))
+
+
+# the exchange step used to be an all-reduce; keep the old name importable
+permanent_allreduce = permanent_allgather

@@ -3,7 +3,7 @@
 The GPU partial of each rank is stood in for by the oracle's long-double walk
 of exactly the segment range the library assigns to that rank
 (``plan.plan`` + ``plan.segment_range``); everything else -- argument
-resolution, rank -> range mapping, the one all-reduce of four doubles, the
+resolution, rank -> range mapping, the one all-gather of four doubles per rank and their error-free sum, the
 final scaling -- is the product code path of ``piquasso_b200.distributed``.
 """
 
@@ -44,7 +44,7 @@ def _worker(rank, world, port, cases, results):
     distributed._device_partial = _oracle_partial
     out = []
     for a, rows, cols in cases:
-        out.append(complex(distributed.permanent_allreduce(a, rows, cols, device_index=0)))
+        out.append(complex(distributed.permanent_allgather(a, rows, cols, device_index=0)))
     results[rank] = out
     dist.barrier()
     dist.destroy_process_group()

@@ -83,7 +83,7 @@ def test_laplace_goldens_from_compiled_reference():
         assert np.allclose(got, want, rtol=RTOL, atol=1e-13), case["source"]
 
 
-@pytest.mark.parametrize("choice", [1, 2, 212, 122, 222, 132, 232])
+@pytest.mark.parametrize("choice", [1, 2, 22, 32, 42])
 def test_every_kernel_variant_matches_the_arbiter(lib, choice):
     for n in (9, 13, 17, 21):
         a = haar(n, n)
@@ -132,7 +132,9 @@ def test_partition_indexing_segment_sums(lib):
     rng = np.random.default_rng(29)
     cases = [(haar(12, 3), np.ones(12, int), np.ones(12, int), 16, 1),
              (haar(12, 3), np.ones(12, int), np.ones(12, int), 16, 2),
-             (haar(14, 4), np.ones(14, int), np.ones(14, int), 8, 222)]
+             (haar(14, 4), np.ones(14, int), np.ones(14, int), 8, 22),
+             (haar(15, 6), np.ones(15, int), np.ones(15, int), 64, 32),
+             (haar(17, 7), np.ones(17, int), np.ones(17, int), 256, 42)]
     for trial in range(6):
         d = int(rng.integers(3, 8))
         nph = int(rng.integers(4, 11))
@@ -163,17 +165,17 @@ def test_partition_indexing_segment_sums(lib):
 
 def test_partials_of_all_ranks_sum_to_the_whole(lib):
     import torch
-    from piquasso_b200.distributed import _device_partial, finish
+    from piquasso_b200.distributed import _device_partial, combine, finish
     a = np.ascontiguousarray(haar(22, 22), dtype=np.complex128)
     ones = np.ones(22, np.int32)
     whole = complex(permanent(a, ones, ones))
     for nparts in (1, 2, 3, 8):
-        tot = np.zeros(4)
+        quads = []
         for g in range(nparts):
             part = _device_partial(a, ones, ones, g, nparts, 0)
             torch.cuda.synchronize()
-            tot += part.cpu().numpy()
-        assert relerr(finish(tot, 22), whole) < 1e-13
+            quads.append(part.cpu().numpy())
+        assert relerr(finish(combine(quads), 22), whole) < 1e-13
 
 
 def test_closed_forms_up_to_n32():

@@ -32,6 +32,7 @@ def test_plan_all_ones():
         assert p["flops_per_term"] == 8 * n + 2
         assert p["sum_rows"] == n and p["trivial"] == 0
     assert plan.plan(np.ones(40, int), np.ones(40, int))["kernel"] == 2
+    assert plan.plan(np.ones(20, int), np.ones(20, int))["kernel"] == 1  # small: generic walk
     assert plan.plan([2, 1, 0, 3], [1, 1, 4, 0])["kernel"] == 1
 
 
@@ -141,10 +142,14 @@ def test_compute_without_a_device_fails_loudly(lib):
         permanent_laplace(haar(3, 1), [1, 1, 0], [1, 1, 1])
 
 
-def test_finish_scaling():
-    from piquasso_b200.distributed import finish
+def test_finish_scaling_and_error_free_combine():
+    from piquasso_b200.distributed import combine, finish
     v = finish([3.0, 0.5, -8.0, 0.0], 4)
     assert v == complex(3.5 / 8, -1.0)
+    # partials far larger than their sum: a plain sum of the hi parts returns 0
+    quads = [[1e20, 0.0, 1.0, 0.0], [1.0, 1e-20, 1e-17, 0.0], [-1e20, 0.0, -1.0, 0.0]]
+    out = combine(quads)
+    assert out[0] + out[1] == 1.0 and out[2] + out[3] == 1e-17
 
 
 def test_pybind_module_surface():
