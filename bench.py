@@ -49,9 +49,11 @@ import numpy as np  # noqa: E402
 METRIC = "n40_c128_permanent_gray_code_terms_per_s"
 UNIT = "terms/s"
 NOMINAL_FP64_TFLOPS = 37.2  # 148 SM x 64 lanes x 2 flop x 1.965 GHz
-# DRAM bytes per walk launch from the ncu --set full capture in profiles/ (the
-# whole working set is the 26 KB matrix, staged once per CTA)
-TRAFFIC_BYTES_PER_LAUNCH = None
+# dram__bytes_read.sum + dram__bytes_write.sum of the walk kernel, from the
+# `ncu --set full` capture summarised in profiles/r01_ncu_summary.md (n=30
+# launch: 61.4 KB read, 0 written; the n=40 launch stages the same kind of
+# <= 26 KB matrix once per CTA out of L2).  Algorithmic bytes are n^2*16 + 32.
+TRAFFIC_BYTES_PER_LAUNCH = 61440
 
 
 def haar_matrix(n, seed):
