@@ -237,6 +237,9 @@ def main_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION/INFO print there)
+        if not os.environ.get("PQ_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
