@@ -19,6 +19,15 @@ from . import _lib
 
 __all__ = ["permanent_laplace_batch", "generate_samples"]
 
+# wall-clock split of generate_samples (seconds), for tools/sampler_bench.py
+TIMERS = {}
+
+
+def _tick(name, t0):
+    import time
+    TIMERS[name] = TIMERS.get(name, 0.0) + (time.perf_counter() - t0)
+
+
 
 def permanent_laplace_batch(matrices, rows_list, cols_list):
     """``[permanent_laplace(m, r, c) for m, r, c in zip(...)]`` in one call.
@@ -117,7 +126,9 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
         current_input = np.zeros((nb, d), dtype=int)
         to_shrink = [np.copy(first_quantized) for _ in range(nb)]
         arange_d = np.arange(d)
+        import time
         for photon in range(n):
+            t0 = time.perf_counter()
             mats, rws, cls, nz = [], [], [], []
             live = [s for s in range(nb) if not rejected[start + s, photon]]
             for s in live:
@@ -133,7 +144,11 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
                 rws.append(sample[s][out_nz])
                 cls.append(current_input[s][in_nz])
                 nz.append(arange_d[in_nz])
+            _tick("host: grow input + filter", t0)
+            t0 = time.perf_counter()
             partials = permanent_laplace_batch(mats, rws, cls)
+            _tick("permanent_laplace_batch (pack + plan + GPU)", t0)
+            t0 = time.perf_counter()
             for i, s in enumerate(live):
                 # _calculate_pmf (sampling.py:736-749): pmf[m] = |sum_j in_j p_j U[m, nz_j]|^2
                 weights = current_input[s][nz[i]] * partials[i]
@@ -142,5 +157,6 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
                 pmf = pmf / pmf.sum()
                 index = rngs[s].choice(arange_d, p=pmf)
                 sample[s, index] += 1
+            _tick("host: pmf + rng.choice", t0)
         samples_all.extend(tuple(int(x) for x in row) for row in sample)
     return samples_all

@@ -1,0 +1,45 @@
+"""Config 4 (BASELINE.json): Clifford-Clifford boson sampling, 100 modes / 25 photons.
+python tools/sampler_bench.py SHOTS [MODES PHOTONS]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from scipy.stats import unitary_group
+from piquasso_b200 import _lib, sampling
+
+shots = int(sys.argv[1]); d = int(sys.argv[2]) if len(sys.argv) > 2 else 100; n = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+U = unitary_group.rvs(d, random_state=d)
+inp = np.array([1] * n + [0] * (d - n))
+lib = _lib.load()
+sampling.generate_samples(inp[:], 2, U, 123)  # warm-up
+sampling.TIMERS.clear()
+t = time.perf_counter()
+samples = sampling.generate_samples(inp, shots, U, 123)
+dt = time.perf_counter() - t
+print(f"{shots} shots, {d} modes, {n} photons: {dt:.2f} s  ({dt/shots*1e3:.2f} ms/shot)", flush=True)
+for k, v in sampling.TIMERS.items():
+    print(f"   {k}: {v:.3f} s")
+print("first samples:", samples[:2])
+if "--check" in sys.argv:
+    import oracle
+    # reference-style sequential sampler on the oracle's permanent_laplace for the first shots
+    def ref_sample(seed):
+        rng = np.random.default_rng(seed)
+        sample = np.zeros(d, dtype=int); cur = np.zeros(d, dtype=int); shrink = np.repeat(np.arange(d), inp)
+        for _ in range(n):
+            ri = rng.choice(len(shrink)); cur[shrink[ri]] += 1; shrink = np.delete(shrink, ri)
+            nz = cur > 0; oz = sample > 0
+            part = oracle.ref_permanent_laplace(U[np.ix_(oz, nz)], sample[oz], cur[nz])
+            idx = np.arange(d)[nz]
+            pmf = np.empty(d)
+            for m in range(d):
+                p = 0.0
+                for j in range(len(part)):
+                    p += cur[idx[j]] * part[j] * U[m, idx[j]]
+                pmf[m] = np.abs(p) ** 2
+            pmf = pmf / pmf.sum()
+            sample[rng.choice(np.arange(d), p=pmf)] += 1
+        return tuple(int(x) for x in sample)
+    ncheck = int(os.environ.get("NCHECK", "3"))
+    t = time.perf_counter()
+    ok = all(ref_sample(123 + i) == samples[i] for i in range(ncheck))
+    print(f"first {ncheck} shots identical to the reference algorithm on the compiled reference: {ok}  ({(time.perf_counter()-t)/ncheck:.2f} s/shot on CPU)")
