@@ -91,6 +91,21 @@ int pq_perm_laplace_batch_c128(int nprob, const double *A, const int64_t *a_off,
                                int32_t *out_len);
 
 /* ---------------------------------------------------------------------
+ * One photon step of the Clifford-Clifford sampler for `nshots` independent
+ * shots sharing one d x d interferometer U (row-major complex128).  For shot s,
+ * with the output occupations placed so far out_occ[s*d .. ] and the input
+ * occupations grown so far in_occ[s*d .. ], computes what _calculate_pmf
+ * (piquasso/_simulators/passive/sampling.py:723-749) computes before
+ * normalisation:   pmf[s*d + m] = | sum_j in_j * partial_j * U[m, nz_j] |^2,
+ * partial = permanent_laplace(U[out>0][:, in>0], out[out>0], in[in>0]).
+ * Zero filtering, the batched Laplace walk and the pmf assembly all happen
+ * inside the call (the pmf on the device, as an epilogue of the walk); the
+ * host keeps the per-shot RNG and draws from the returned rows.
+ * ------------------------------------------------------------------- */
+int pq_sampler_pmf_c128(const double *U, int d, int nshots, const int32_t *out_occ,
+                        const int32_t *in_occ, double *pmf);
+
+/* ---------------------------------------------------------------------
  * Partitioned permanent: the piece of one permanent that rank `part` of
  * `nparts` owns.  The term space [0, idx_max) (src/permanent.cpp:131-142) is
  * cut into equal-length Gray-code segments (one per GPU thread; the

@@ -21,7 +21,7 @@ OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libpqperm.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+NVCC_FLAGS = ARCH + (["-DPQ_TUNING"] if os.environ.get("PQ_TUNING") else []) + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
                      "-Xcompiler", "-Wall", "-Xcompiler", "-Wextra"]
 
 # column ranges of the binary constant-bank kernel, one translation unit each
@@ -38,6 +38,7 @@ def _nvcc() -> str:
 def _units():
     units = [
         ("api", "pqperm_api.cu", []),
+        ("api_laplace", "pqperm_api_laplace.cu", []),
         ("plan", "pqperm_plan.cpp", []),
         ("generic", "pqperm_kernels_generic.cu", []),
         ("laplace_unit", "pqperm_kernels_laplace.cu", ["-DPQ_LAP_UNIT=1"]),

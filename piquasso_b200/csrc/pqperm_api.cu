@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/pqperm.h"
+#include "pqperm_ctx.h"
 #include "pqperm_launch.h"
 #include "pqperm_plan.h"
 
@@ -47,17 +48,18 @@ cudaError_t launch_binary(int nc, int B, const WalkParams &P, const double2 *d_A
 using namespace pqperm;
 
 // ---------------------------------------------------------------------------
-// error plumbing
+// error plumbing (declared in pqperm_ctx.h)
 // ---------------------------------------------------------------------------
 static thread_local std::string g_last_error;
 
-static int fail(int code, const std::string &msg)
+namespace pqperm {
+int fail(int code, const std::string &msg)
 {
     g_last_error = msg;
     return code;
 }
 
-static int fail_cuda(cudaError_t e, const char *what)
+int fail_cuda(cudaError_t e, const char *what)
 {
     g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
     // a missing driver / device must read as "no device", not as a CUDA bug
@@ -66,13 +68,7 @@ static int fail_cuda(cudaError_t e, const char *what)
         return PQ_ERR_NO_DEVICE;
     return PQ_ERR_CUDA;
 }
-
-#define PQ_CUDA(call)                                                                   \
-    do {                                                                                \
-        cudaError_t e__ = (call);                                                       \
-        if (e__ != cudaSuccess)                                                         \
-            return fail_cuda(e__, #call);                                               \
-    } while (0)
+} // namespace pqperm
 
 extern "C" const char *pq_last_error(void) { return g_last_error.c_str(); }
 
@@ -81,46 +77,14 @@ extern "C" const char *pq_last_error(void) { return g_last_error.c_str(); }
 // ---------------------------------------------------------------------------
 namespace pqperm {
 
-constexpr int kMaxGrid = 148 * 32 * 2;
-constexpr int kTimingRing = 64;
-
-struct DeviceCtx {
-    int device = -1;
-    int num_sms = 148;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t ev_up = nullptr;   // uploads of the last enqueue have left h_pinned
-    bool up_pending = false;
-    double *d_A2 = nullptr;        // (kMaxDigits+1) x kMaxCols double2
-    double *d_partials = nullptr;  // kMaxGrid x 4
-    double *d_out = nullptr;       // 4 doubles
-    unsigned long long *d_counter = nullptr;  // segment dispenser of the walk kernels
-    uint8_t *d_sched = nullptr;    // kMaxSegLenNary
-    double *d_wtab = nullptr;      // kMaxSegLenNary
-    double *d_binom = nullptr;     // kMaxDigits * 256
-    double *h_pinned = nullptr;    // staging: A2 + out
-    double last_kernel_ms = -1.0;
-    bool ready = false;
-    uint64_t resident_job = 0;     // id of the pq_perm_job whose inputs sit in the buffers
-    cudaEvent_t ring0[kTimingRing], ring1[kTimingRing];  // event pairs around the kernels
-    uint64_t ring_next = 0;
-    // growable buffers of the batched Laplace path
-    void *d_lap[4] = {nullptr, nullptr, nullptr, nullptr};   // prob, A2, partials, out
-    size_t d_lap_cap[4] = {0, 0, 0, 0};
-    void *h_lap[3] = {nullptr, nullptr, nullptr};            // prob, A2, out (pinned)
-    size_t h_lap_cap[3] = {0, 0, 0};
-};
-
-static std::mutex g_mu;                 // one caller at a time (GIL-held callers anyway)
-static std::vector<std::unique_ptr<DeviceCtx>> g_ctx;
-static std::vector<int> g_devices = {0};
-static std::atomic<int64_t> g_launches{0};
+std::mutex g_mu;
+std::vector<std::unique_ptr<DeviceCtx>> g_ctx;
+std::vector<int> g_devices = {0};
+std::atomic<int64_t> g_launches{0};
 static int g_kernel_choice = 0;
 static int64_t g_seg_len_hint = 0;
 
-constexpr size_t kA2Doubles = (size_t)(kMaxDigits + 1) * kMaxCols * 2;
-
-static int ctx_get(int device, DeviceCtx **out)
+int ctx_get(int device, DeviceCtx **out)
 {
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -161,6 +125,34 @@ static int ctx_get(int device, DeviceCtx **out)
         c->ready = true;
     }
     *out = c;
+    return PQ_OK;
+}
+
+int grow_dev(DeviceCtx *c, int slot, size_t bytes)
+{
+    if (c->d_lap_cap[slot] >= bytes)
+        return PQ_OK;
+    if (c->d_lap[slot])
+        cudaFree(c->d_lap[slot]);
+    c->d_lap[slot] = nullptr;
+    c->d_lap_cap[slot] = 0;
+    const size_t cap = bytes + bytes / 2 + 4096;
+    PQ_CUDA(cudaMalloc(&c->d_lap[slot], cap));
+    c->d_lap_cap[slot] = cap;
+    return PQ_OK;
+}
+
+int grow_host(DeviceCtx *c, int slot, size_t bytes)
+{
+    if (c->h_lap_cap[slot] >= bytes)
+        return PQ_OK;
+    if (c->h_lap[slot])
+        cudaFreeHost(c->h_lap[slot]);
+    c->h_lap[slot] = nullptr;
+    c->h_lap_cap[slot] = 0;
+    const size_t cap = bytes + bytes / 2 + 4096;
+    PQ_CUDA(cudaMallocHost(&c->h_lap[slot], cap));
+    c->h_lap_cap[slot] = cap;
     return PQ_OK;
 }
 
@@ -771,269 +763,3 @@ extern "C" int pq_kernel_ms_history(int device, double *out, int max)
     return n;
 }
 
-// ---------------------------------------------------------------------------
-// permanent_laplace: single call and batch (kernels: pqperm_laplace.cuh)
-// ---------------------------------------------------------------------------
-namespace pqperm {
-
-static int grow_dev(DeviceCtx *c, int slot, size_t bytes)
-{
-    if (c->d_lap_cap[slot] >= bytes)
-        return PQ_OK;
-    if (c->d_lap[slot])
-        cudaFree(c->d_lap[slot]);
-    c->d_lap[slot] = nullptr;
-    c->d_lap_cap[slot] = 0;
-    const size_t cap = bytes + bytes / 2 + 4096;
-    PQ_CUDA(cudaMalloc(&c->d_lap[slot], cap));
-    c->d_lap_cap[slot] = cap;
-    return PQ_OK;
-}
-
-static int grow_host(DeviceCtx *c, int slot, size_t bytes)
-{
-    if (c->h_lap_cap[slot] >= bytes)
-        return PQ_OK;
-    if (c->h_lap[slot])
-        cudaFreeHost(c->h_lap[slot]);
-    c->h_lap[slot] = nullptr;
-    c->h_lap_cap[slot] = 0;
-    const size_t cap = bytes + bytes / 2 + 4096;
-    PQ_CUDA(cudaMallocHost(&c->h_lap[slot], cap));
-    c->h_lap_cap[slot] = cap;
-    return PQ_OK;
-}
-
-struct LapItem {
-    int index;   // problem index in the caller's batch
-    Plan plan;
-};
-
-// Run one group of problems that share a kernel variant (same S, NCL, unit
-// flag); results are scattered into the caller's `out`.
-static int laplace_group(DeviceCtx *c, std::vector<LapItem> &items, int S, int NCL,
-                         bool unitcols, const int32_t *C, const int32_t *cols,
-                         const int64_t *c_off, double *out, const int64_t *o_off)
-{
-    const int n = (int)items.size();
-    const int NCP = S * NCL, ncp1 = NCP + 1;
-    // CTAs per problem: enough to cover its segments, bounded so that the
-    // whole group is a few waves of the machine
-    const int groups_per_block = kLapThreads / S;
-    const long long wave = (long long)c->num_sms * 8;
-    long long budget = std::max<long long>(1, (4 * wave) / n);
-    size_t a2_elems = 0;
-    int total_blocks = 0, max_D = 0;
-    int rc = grow_host(c, 0, sizeof(LapProblem) * (size_t)n);
-    if (rc)
-        return rc;
-    LapProblem *hp = reinterpret_cast<LapProblem *>(c->h_lap[0]);
-    for (int i = 0; i < n; i++) {
-        const Plan &pl = items[i].plan;
-        LapProblem &q = hp[i];
-        std::memset(&q, 0, sizeof(q));
-        q.a_off = (long long)a2_elems;
-        q.nseg = pl.nseg;
-        long long nb = (pl.nseg + groups_per_block - 1) / groups_per_block;
-        nb = std::max<long long>(1, std::min(nb, budget));
-        q.first_block = total_blocks;
-        q.nblocks = (int)nb;
-        q.D = pl.D;
-        q.q = pl.q;
-        q.W = (int)pl.W;
-        q.exp2 = pl.sum_rows - 1;
-        for (int d = 0; d < pl.D; d++)
-            q.mult[d] = (uint8_t)pl.mult[d];
-        for (int j = 0; j < NCP; j++)
-            q.colmult[j] = (uint8_t)pl.colmult[j];
-        total_blocks += (int)nb;
-        a2_elems += (size_t)(pl.D + 1) * NCP;
-        max_D = std::max(max_D, pl.D);
-    }
-    rc = grow_host(c, 1, a2_elems * sizeof(double2));
-    if (rc)
-        return rc;
-    double *ha = reinterpret_cast<double *>(c->h_lap[1]);
-    for (int i = 0; i < n; i++)
-        std::memcpy(ha + 2 * hp[i].a_off, items[i].plan.A2.data(),
-                    items[i].plan.A2.size() * sizeof(double));
-    const size_t out_bytes = (size_t)n * ncp1 * sizeof(double2);
-    if ((rc = grow_host(c, 2, out_bytes)) || (rc = grow_dev(c, 0, sizeof(LapProblem) * (size_t)n)) ||
-        (rc = grow_dev(c, 1, a2_elems * sizeof(double2))) ||
-        (rc = grow_dev(c, 2, (size_t)total_blocks * ncp1 * sizeof(double2))) ||
-        (rc = grow_dev(c, 3, out_bytes)))
-        return rc;
-    cudaStream_t st = c->stream;
-    PQ_CUDA(cudaMemcpyAsync(c->d_lap[0], hp, sizeof(LapProblem) * (size_t)n,
-                            cudaMemcpyHostToDevice, st));
-    PQ_CUDA(cudaMemcpyAsync(c->d_lap[1], ha, a2_elems * sizeof(double2),
-                            cudaMemcpyHostToDevice, st));
-    LapParams P;
-    P.prob = reinterpret_cast<const LapProblem *>(c->d_lap[0]);
-    P.A2 = reinterpret_cast<const double2 *>(c->d_lap[1]);
-    P.partials = reinterpret_cast<double2 *>(c->d_lap[2]);
-    P.out = reinterpret_cast<double2 *>(c->d_lap[3]);
-    P.nprob = n;
-    const size_t smem = (size_t)(max_D + 1) * NCP * sizeof(double2);
-    PQ_CUDA(cudaEventRecord(c->ev0, st));
-    cudaError_t e = launch_laplace(S, NCL, unitcols, P, total_blocks, smem, st);
-    if (e != cudaSuccess)
-        return fail_cuda(e, "launch laplace_walk_kernel");
-    e = launch_laplace_reduce(P, ncp1, st);
-    if (e != cudaSuccess)
-        return fail_cuda(e, "launch laplace_reduce_kernel");
-    g_launches += 2;
-    PQ_CUDA(cudaEventRecord(c->ev1, st));
-    PQ_CUDA(cudaMemcpyAsync(c->h_lap[2], c->d_lap[3], out_bytes, cudaMemcpyDeviceToHost, st));
-    PQ_CUDA(cudaStreamSynchronize(st));
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
-        c->last_kernel_ms = (c->last_kernel_ms < 0 ? 0.0 : c->last_kernel_ms) + ms;
-    // scatter: compact column k -> original column src_col[k]; columns with
-    // multiplicity 0 receive the full product (reference quirk)
-    const double *ho = reinterpret_cast<const double *>(c->h_lap[2]);
-    for (int i = 0; i < n; i++) {
-        const Plan &pl = items[i].plan;
-        const int b = items[i].index;
-        const double *res = ho + (size_t)i * ncp1 * 2;
-        double *dst = out + 2 * o_off[b];
-        const int32_t *cm = cols + c_off[b];
-        int k = 0;
-        for (int j = 0; j < C[b]; j++) {
-            if (cm[j] > 0) {
-                dst[2 * j] = res[2 * k];
-                dst[2 * j + 1] = res[2 * k + 1];
-                k++;
-            } else {
-                dst[2 * j] = res[2 * NCP];
-                dst[2 * j + 1] = res[2 * NCP + 1];
-            }
-        }
-        (void)pl;
-    }
-    return PQ_OK;
-}
-
-static int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off,
-                                const int32_t *R, const int32_t *C, const int32_t *rows,
-                                const int64_t *r_off, const int32_t *cols,
-                                const int64_t *c_off, double *out, const int64_t *o_off,
-                                int32_t *out_len)
-{
-    // plan every problem first: validation and early-outs need no device
-    std::vector<LapItem> items;
-    items.reserve(nprob);
-    std::string err;
-    PlanOptions o = plan_options(148);
-    o.laplace = true;
-    o.kernel_choice = 1;
-    o.batch = std::max(1, nprob);
-    int num_sms = 148;
-    DeviceCtx *c = nullptr;
-    for (int b = 0; b < nprob; b++) {
-        if (R[b] < 0 || C[b] < 0)
-            return fail(PQ_ERR_BAD_ARG, "negative shape in batch");
-        LapItem it;
-        it.index = b;
-        // cheap structural pass first (no matrix) to catch the early-out
-        int rc = make_plan(nullptr, R[b], C[b], rows + r_off[b], cols + c_off[b], o, it.plan, err);
-        if (rc)
-            return fail(rc, err);
-        if (it.plan.trivial) {
-            out[2 * o_off[b]] = 1.0; // src/permanent_laplace.cpp:52-57
-            out[2 * o_off[b] + 1] = 0.0;
-            out_len[b] = 1;
-            continue;
-        }
-        if (!c) {
-            rc = ctx_get(g_devices[0], &c);
-            if (rc)
-                return rc;
-            num_sms = c->num_sms;
-            o.num_sms = num_sms;
-        }
-        rc = make_plan(A + 2 * a_off[b], R[b], C[b], rows + r_off[b], cols + c_off[b], o,
-                       it.plan, err);
-        if (rc)
-            return fail(rc, err);
-        out_len[b] = C[b];
-        items.push_back(std::move(it));
-    }
-    if (items.empty())
-        return PQ_OK;
-    c->last_kernel_ms = -1.0;
-    // group by kernel variant
-    std::vector<char> done(items.size(), 0);
-    for (size_t i = 0; i < items.size(); i++) {
-        if (done[i])
-            continue;
-        const LapVariant v = laplace_variant(items[i].plan.NC);
-        const bool unit = items[i].plan.unitcols;
-        std::vector<LapItem> group;
-        for (size_t k = i; k < items.size(); k++) {
-            if (done[k])
-                continue;
-            const LapVariant vk = laplace_variant(items[k].plan.NC);
-            if (vk.S == v.S && vk.NCL == v.NCL && items[k].plan.unitcols == unit) {
-                group.push_back(std::move(items[k]));
-                done[k] = 1;
-            }
-        }
-        const int rc = laplace_group(c, group, v.S, v.NCL, unit, C, cols, c_off, out, o_off);
-        if (rc)
-            return rc;
-    }
-    return PQ_OK;
-}
-
-} // namespace pqperm
-
-extern "C" int pq_perm_laplace_batch_c128(int nprob, const double *A, const int64_t *a_off,
-                                          const int32_t *R, const int32_t *C,
-                                          const int32_t *rows, const int64_t *r_off,
-                                          const int32_t *cols, const int64_t *c_off,
-                                          double *out, const int64_t *o_off,
-                                          int32_t *out_len)
-{
-    if (nprob < 0 || (nprob > 0 && (!a_off || !R || !C || !r_off || !c_off || !out ||
-                                    !o_off || !out_len)))
-        return fail(PQ_ERR_BAD_ARG, "null pointer in batch call");
-    if (nprob == 0)
-        return PQ_OK;
-    std::lock_guard<std::mutex> lock(g_mu);
-    return laplace_batch_locked(nprob, A, a_off, R, C, rows, r_off, cols, c_off, out, o_off,
-                                out_len);
-}
-
-extern "C" int pq_perm_laplace_c128(const double *A, int R, int C, const int32_t *rows,
-                                    const int32_t *cols, double *out, int *out_len)
-{
-    if (!out || !out_len || (R > 0 && C > 0 && !A))
-        return fail(PQ_ERR_BAD_ARG, "null pointer");
-    const int64_t zero = 0;
-    const int32_t r32 = R, c32 = C;
-    int32_t len = 0;
-    const int rc = pq_perm_laplace_batch_c128(1, A, &zero, &r32, &c32, rows, &zero, cols, &zero,
-                                              out, &zero, &len);
-    if (rc)
-        return rc;
-    *out_len = len;
-    return PQ_OK;
-}
-
-extern "C" int pq_perm_laplace_c64(const float *A, int R, int C, const int32_t *rows,
-                                   const int32_t *cols, float *out, int *out_len)
-{
-    if (!out || !out_len || (R > 0 && C > 0 && !A))
-        return fail(PQ_ERR_BAD_ARG, "null pointer");
-    std::vector<double> Ad((size_t)(R > 0 ? R : 0) * (C > 0 ? C : 0) * 2);
-    for (size_t i = 0; i < Ad.size(); i++)
-        Ad[i] = (double)A[i];
-    std::vector<double> o(2 * (size_t)(C > 0 ? C : 1));
-    const int rc = pq_perm_laplace_c128(Ad.data(), R, C, rows, cols, o.data(), out_len);
-    if (rc)
-        return rc;
-    for (int i = 0; i < 2 * *out_len; i++)
-        out[i] = (float)o[i];
-    return PQ_OK;
-}

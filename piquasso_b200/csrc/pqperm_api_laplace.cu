@@ -1,0 +1,481 @@
+// pqperm_api_laplace.cu -- host side of permanent_laplace: single call, batch
+// and the sampler's photon step (kernels: pqperm_laplace.cuh).
+//
+// A batch is described problem by problem with a lean planner (no allocation
+// per problem), bucketed by kernel variant (lanes per segment S, columns per
+// lane NCL, unit-column flavour), and each bucket is one walk launch + one
+// reduce launch (+ the pmf epilogue for the sampler).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pqperm_ctx.h"
+#include "pqperm_launch.h"
+
+using namespace pqperm;
+
+namespace {
+
+constexpr int kLapSegLen = 64; // terms per segment (<= kLapMaxSegLen)
+
+// What the lean planner extracts from one problem's multiplicity vectors
+// (zeros allowed).  Restates src/permanent_laplace.cpp:49-118 of the reference
+// plus the compaction of pqperm_plan.cpp.
+struct LapShape {
+    int trivial;             // reference early-out: result is [1]
+    int D, NC, M;            // digits, active columns, sum of column multiplicities
+    int pinned;              // row pinned to delta = +1
+    int sum_rows;
+    bool unit;
+    int src_row[kMaxDigits]; // row feeding digit d
+    int mult[kMaxDigits];
+    int src_col[kMaxCols];
+    int colmult[kMaxCols];
+};
+
+int lap_shape(int R, int C, const int32_t *rows, const int32_t *cols, LapShape &sh,
+              std::string &err)
+{
+    long long sr = 0, sc = 0;
+    for (int i = 0; i < R; i++) {
+        if (rows[i] < 0) {
+            err = "negative row multiplicity";
+            return PQ_ERR_BAD_ARG;
+        }
+        sr += rows[i];
+    }
+    for (int j = 0; j < C; j++) {
+        if (cols[j] < 0) {
+            err = "negative column multiplicity";
+            return PQ_ERR_BAD_ARG;
+        }
+        sc += cols[j];
+    }
+    sh.sum_rows = (int)sr;
+    sh.trivial = (R == 0 || C == 0 || sr == 0 || sc == 0); // src/permanent_laplace.cpp:52-57
+    if (sh.trivial)
+        return PQ_OK;
+    int min_idx = 0, minelem = 0; // :59-69, first smallest non-zero multiplicity
+    for (int i = 0; i < R; i++)
+        if (minelem == 0 || (rows[i] < minelem && rows[i] != 0)) {
+            minelem = rows[i];
+            min_idx = i;
+        }
+    sh.pinned = min_idx;
+    sh.D = 0;
+    double idx_max = 1.0;
+    for (int i = 0; i < R; i++) {
+        const int r = rows[i] - (i == min_idx ? 1 : 0);
+        if (r == 0)
+            continue;
+        if (r > kMaxMultiplicity || sh.D >= kMaxDigits) {
+            err = "more than 64 active rows or a multiplicity above 254";
+            return PQ_ERR_TOO_LARGE;
+        }
+        sh.src_row[sh.D] = i;
+        sh.mult[sh.D] = r;
+        sh.D++;
+        idx_max *= (r + 1);
+    }
+    if (idx_max > 4.6e18) {
+        err = "term space exceeds 2^62";
+        return PQ_ERR_TOO_LARGE;
+    }
+    sh.NC = 0;
+    sh.M = 0;
+    sh.unit = true;
+    for (int j = 0; j < C; j++) {
+        if (cols[j] == 0)
+            continue;
+        if (cols[j] > kMaxMultiplicity || sh.NC >= kMaxCols) {
+            err = "more than 64 active columns or a multiplicity above 254";
+            return PQ_ERR_TOO_LARGE;
+        }
+        sh.src_col[sh.NC] = j;
+        sh.colmult[sh.NC] = cols[j];
+        sh.M += cols[j];
+        if (cols[j] != 1)
+            sh.unit = false;
+        sh.NC++;
+    }
+    return PQ_OK;
+}
+
+// Fills the walk parameters of a described problem: digits 0..q-1 are walked
+// inside a segment of W <= kLapSegLen terms, the rest index the segments.
+void lap_fill(const LapShape &sh, int ncp, LapProblem &q)
+{
+    std::memset(&q, 0, sizeof(q));
+    q.D = sh.D;
+    int qd = 0;
+    long long W = 1, total = 1;
+    for (int d = 0; d < sh.D; d++) {
+        total *= (sh.mult[d] + 1);
+        if (qd == d && qd < kMaxLowDigits && W * (sh.mult[d] + 1) <= kLapSegLen) {
+            W *= (sh.mult[d] + 1);
+            qd++;
+        }
+        q.mult[d] = (uint8_t)sh.mult[d];
+    }
+    q.q = qd;
+    q.W = (int)W;
+    q.nseg = total / W;
+    q.exp2 = sh.sum_rows - 1;
+    q.nc = sh.NC;
+    for (int j = 0; j < ncp; j++)
+        q.colmult[j] = (uint8_t)(j < sh.NC ? sh.colmult[j] : 1);
+}
+
+struct Bucket {
+    int S = 0, NCL = 0;
+    bool unit = false;
+    std::vector<LapProblem> probs;
+    std::vector<double> a2;   // packed mode
+    int max_D = 0;
+};
+
+// buckets[(S index) * 17 * 2 + NCL * 2 + unit]
+struct Buckets {
+    std::vector<Bucket> b;
+    Buckets() : b(3 * 17 * 2) {}
+    Bucket &get(const LapVariant &v, bool unit)
+    {
+        const int si = v.S == 1 ? 0 : (v.S == 2 ? 1 : 2);
+        Bucket &k = b[(si * 17 + v.NCL) * 2 + (unit ? 1 : 0)];
+        k.S = v.S;
+        k.NCL = v.NCL;
+        k.unit = unit;
+        return k;
+    }
+    void reset()
+    {
+        for (Bucket &k : b) {
+            k.probs.clear();
+            k.a2.clear();
+            k.max_D = 0;
+        }
+    }
+};
+Buckets g_buckets; // guarded by g_mu; keeps its capacity between calls
+
+struct Epilogue {
+    const double2 *d_U = nullptr; // gather mode / sampler: matrix on the device
+    int ldu = 0;
+    double *pmf = nullptr;        // sampler: host [nshots][ldu], row = LapProblem.tag
+};
+
+// One bucket = one walk launch + one reduce launch (+ pmf epilogue).  Without
+// an epilogue the compact results land in c->h_lap[2] ([n][NCP+1] complex).
+int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
+{
+    const int n = (int)bk.probs.size();
+    const int NCP = bk.S * bk.NCL, ncp1 = NCP + 1;
+    const int groups_per_block = kLapThreads / bk.S;
+    const long long wave = (long long)c->num_sms * 8;
+    const long long budget = std::max<long long>(1, (4 * wave) / n);
+    int total_blocks = 0;
+    for (LapProblem &q : bk.probs) {
+        long long nb = (q.nseg + groups_per_block - 1) / groups_per_block;
+        nb = std::max<long long>(1, std::min(nb, budget));
+        q.first_block = total_blocks;
+        q.nblocks = (int)nb;
+        total_blocks += (int)nb;
+    }
+    const size_t out_bytes = (size_t)n * ncp1 * sizeof(double2);
+    int rc;
+    if ((rc = grow_dev(c, 0, sizeof(LapProblem) * (size_t)n)) ||
+        (rc = grow_dev(c, 2, (size_t)total_blocks * ncp1 * sizeof(double2))) ||
+        (rc = grow_dev(c, 3, out_bytes)))
+        return rc;
+    cudaStream_t st = c->stream;
+    PQ_CUDA(cudaMemcpyAsync(c->d_lap[0], bk.probs.data(), sizeof(LapProblem) * (size_t)n,
+                            cudaMemcpyHostToDevice, st));
+    LapParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.prob = reinterpret_cast<const LapProblem *>(c->d_lap[0]);
+    if (epi && epi->d_U) {
+        P.U = epi->d_U;
+        P.ldu = epi->ldu;
+    } else {
+        if ((rc = grow_dev(c, 1, bk.a2.size() * sizeof(double))))
+            return rc;
+        PQ_CUDA(cudaMemcpyAsync(c->d_lap[1], bk.a2.data(), bk.a2.size() * sizeof(double),
+                                cudaMemcpyHostToDevice, st));
+        P.A2 = reinterpret_cast<const double2 *>(c->d_lap[1]);
+    }
+    P.partials = reinterpret_cast<double2 *>(c->d_lap[2]);
+    P.out = reinterpret_cast<double2 *>(c->d_lap[3]);
+    P.nprob = n;
+    const size_t smem = (size_t)(bk.max_D + 1) * NCP * sizeof(double2);
+    PQ_CUDA(cudaEventRecord(c->ev0, st));
+    cudaError_t e = launch_laplace(bk.S, bk.NCL, bk.unit, P, total_blocks, smem, st);
+    if (e != cudaSuccess)
+        return fail_cuda(e, "launch laplace_walk_kernel");
+    e = launch_laplace_reduce(P, ncp1, st);
+    if (e != cudaSuccess)
+        return fail_cuda(e, "launch laplace_reduce_kernel");
+    g_launches += 2;
+    void *h_dst = nullptr;
+    size_t bytes = 0;
+    const void *d_src = nullptr;
+    if (epi && epi->pmf) {
+        bytes = (size_t)n * epi->ldu * sizeof(double);
+        if ((rc = grow_dev(c, 5, bytes)) || (rc = grow_host(c, 3, bytes)))
+            return rc;
+        e = launch_sampler_pmf(P, ncp1, epi->d_U, epi->ldu,
+                               reinterpret_cast<double *>(c->d_lap[5]), st);
+        if (e != cudaSuccess)
+            return fail_cuda(e, "launch sampler_pmf_kernel");
+        g_launches += 1;
+        h_dst = c->h_lap[3];
+        d_src = c->d_lap[5];
+    } else {
+        bytes = out_bytes;
+        if ((rc = grow_host(c, 2, bytes)))
+            return rc;
+        h_dst = c->h_lap[2];
+        d_src = c->d_lap[3];
+    }
+    PQ_CUDA(cudaEventRecord(c->ev1, st));
+    PQ_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    PQ_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
+        c->last_kernel_ms = (c->last_kernel_ms < 0 ? 0.0 : c->last_kernel_ms) + ms;
+    if (epi && epi->pmf) {
+        const double *src = reinterpret_cast<const double *>(c->h_lap[3]);
+        for (int i = 0; i < n; i++)
+            std::memcpy(epi->pmf + (size_t)bk.probs[i].tag * epi->ldu, src + (size_t)i * epi->ldu,
+                        (size_t)epi->ldu * sizeof(double));
+    }
+    return PQ_OK;
+}
+
+int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const int32_t *R,
+                         const int32_t *C, const int32_t *rows, const int64_t *r_off,
+                         const int32_t *cols, const int64_t *c_off, double *out,
+                         const int64_t *o_off, int32_t *out_len)
+{
+    std::string err;
+    LapShape sh;
+    g_buckets.reset();
+    bool any = false;
+    for (int b = 0; b < nprob; b++) {
+        if (R[b] < 0 || C[b] < 0)
+            return fail(PQ_ERR_BAD_ARG, "negative shape in batch");
+        const int32_t *rw = rows + r_off[b], *cl = cols + c_off[b];
+        const int rc = lap_shape(R[b], C[b], rw, cl, sh, err);
+        if (rc)
+            return fail(rc, err);
+        if (sh.trivial) {
+            out[2 * o_off[b]] = 1.0;
+            out[2 * o_off[b] + 1] = 0.0;
+            out_len[b] = 1;
+            continue;
+        }
+        out_len[b] = C[b];
+        const LapVariant v = laplace_variant(sh.NC);
+        Bucket &bk = g_buckets.get(v, sh.unit);
+        const int NCP = v.S * v.NCL;
+        LapProblem q;
+        lap_fill(sh, NCP, q);
+        q.tag = b;
+        q.a_off = (long long)(bk.a2.size() / 2);
+        // compacted, pre-doubled matrix: row 0 = pinned row, rows 1..D = 2 a_d
+        const double *Ab = A + 2 * a_off[b];
+        const size_t base = bk.a2.size();
+        bk.a2.resize(base + (size_t)(sh.D + 1) * NCP * 2, 0.0);
+        double *dst = bk.a2.data() + base;
+        for (int j = 0; j < NCP; j++) {
+            if (j < sh.NC) {
+                const size_t src = ((size_t)sh.pinned * C[b] + sh.src_col[j]) * 2;
+                dst[2 * j] = Ab[src];
+                dst[2 * j + 1] = Ab[src + 1];
+            } else {
+                dst[2 * j] = 1.0; // padding column: s_j == 1 for every term
+            }
+        }
+        for (int d = 0; d < sh.D; d++)
+            for (int j = 0; j < sh.NC; j++) {
+                const size_t src = ((size_t)sh.src_row[d] * C[b] + sh.src_col[j]) * 2;
+                dst[((size_t)(d + 1) * NCP + j) * 2] = 2.0 * Ab[src];
+                dst[((size_t)(d + 1) * NCP + j) * 2 + 1] = 2.0 * Ab[src + 1];
+            }
+        bk.max_D = std::max(bk.max_D, sh.D);
+        bk.probs.push_back(q);
+        any = true;
+    }
+    if (!any)
+        return PQ_OK;
+    DeviceCtx *c = nullptr;
+    int rc = ctx_get(g_devices[0], &c);
+    if (rc)
+        return rc;
+    c->last_kernel_ms = -1.0;
+    for (Bucket &bk : g_buckets.b) {
+        if (bk.probs.empty())
+            continue;
+        rc = run_bucket(c, bk, nullptr);
+        if (rc)
+            return rc;
+        // scatter: compact column k -> original column; columns with multiplicity
+        // 0 receive the full product (reference quirk)
+        const int NCP = bk.S * bk.NCL, ncp1 = NCP + 1;
+        const double *ho = reinterpret_cast<const double *>(c->h_lap[2]);
+        for (size_t i = 0; i < bk.probs.size(); i++) {
+            const int b = bk.probs[i].tag;
+            const double *res = ho + i * ncp1 * 2;
+            double *dst = out + 2 * o_off[b];
+            const int32_t *cm = cols + c_off[b];
+            int k = 0;
+            for (int j = 0; j < C[b]; j++) {
+                const int from = cm[j] > 0 ? k++ : NCP;
+                dst[2 * j] = res[2 * from];
+                dst[2 * j + 1] = res[2 * from + 1];
+            }
+        }
+    }
+    return PQ_OK;
+}
+
+// One photon step of the sampler for nshots shots sharing one interferometer.
+int sampler_pmf_locked(const double *U, int d, int nshots, const int32_t *out_occ,
+                       const int32_t *in_occ, double *pmf)
+{
+    DeviceCtx *c = nullptr;
+    int rc = ctx_get(g_devices[0], &c);
+    if (rc)
+        return rc;
+    std::string err;
+    LapShape sh;
+    g_buckets.reset();
+    bool any = false;
+    for (int s = 0; s < nshots; s++) {
+        const int32_t *oo = out_occ + (size_t)s * d, *io = in_occ + (size_t)s * d;
+        // The shape is taken from the UNFILTERED occupations: dropping the zeros
+        // first (_filter_zeros, sampling.py:711-720) keeps the order of the
+        // remaining modes, so the same row is pinned and the same digits result.
+        rc = lap_shape(d, d, oo, io, sh, err);
+        if (rc)
+            return fail(rc, err);
+        double *prow = pmf + (size_t)s * d;
+        if (sh.trivial) {
+            // permanent_laplace returns [1] (src/permanent_laplace.cpp:52-57) and
+            // _calculate_pmf then uses the first non-zero input mode only
+            int j = -1;
+            for (int m = 0; m < d && j < 0; m++)
+                if (io[m] > 0)
+                    j = m;
+            for (int m = 0; m < d; m++) {
+                double v = 0.0;
+                if (j >= 0) {
+                    const double w = (double)io[j];
+                    const double re = w * U[((size_t)m * d + j) * 2];
+                    const double im = w * U[((size_t)m * d + j) * 2 + 1];
+                    v = re * re + im * im;
+                }
+                prow[m] = v;
+            }
+            continue;
+        }
+        const LapVariant v = laplace_variant(sh.NC);
+        Bucket &bk = g_buckets.get(v, sh.unit);
+        LapProblem q;
+        lap_fill(sh, v.S * v.NCL, q);
+        q.tag = s;
+        q.rowmode[0] = (uint16_t)sh.pinned;
+        for (int k = 0; k < sh.D; k++)
+            q.rowmode[k + 1] = (uint16_t)sh.src_row[k];
+        for (int k = 0; k < sh.NC; k++)
+            q.colmode[k] = (uint16_t)sh.src_col[k];
+        bk.max_D = std::max(bk.max_D, sh.D);
+        bk.probs.push_back(q);
+        any = true;
+    }
+    if (!any)
+        return PQ_OK;
+    const size_t ubytes = (size_t)d * d * sizeof(double2);
+    if ((rc = grow_dev(c, 4, ubytes)))
+        return rc;
+    PQ_CUDA(cudaMemcpyAsync(c->d_lap[4], U, ubytes, cudaMemcpyHostToDevice, c->stream));
+    Epilogue epi;
+    epi.d_U = reinterpret_cast<const double2 *>(c->d_lap[4]);
+    epi.ldu = d;
+    epi.pmf = pmf;
+    c->last_kernel_ms = -1.0;
+    for (Bucket &bk : g_buckets.b) {
+        if (bk.probs.empty())
+            continue;
+        rc = run_bucket(c, bk, &epi);
+        if (rc)
+            return rc;
+    }
+    return PQ_OK;
+}
+
+} // namespace
+
+extern "C" int pq_sampler_pmf_c128(const double *U, int d, int nshots, const int32_t *out_occ,
+                                   const int32_t *in_occ, double *pmf)
+{
+    if (d < 1 || d > 65535 || nshots < 0 || !U || (nshots > 0 && (!out_occ || !in_occ || !pmf)))
+        return fail(PQ_ERR_BAD_ARG, "bad sampler arguments");
+    if (nshots == 0)
+        return PQ_OK;
+    std::lock_guard<std::mutex> lock(g_mu);
+    return sampler_pmf_locked(U, d, nshots, out_occ, in_occ, pmf);
+}
+
+extern "C" int pq_perm_laplace_batch_c128(int nprob, const double *A, const int64_t *a_off,
+                                          const int32_t *R, const int32_t *C,
+                                          const int32_t *rows, const int64_t *r_off,
+                                          const int32_t *cols, const int64_t *c_off,
+                                          double *out, const int64_t *o_off,
+                                          int32_t *out_len)
+{
+    if (nprob < 0 || (nprob > 0 && (!a_off || !R || !C || !r_off || !c_off || !out ||
+                                    !o_off || !out_len)))
+        return fail(PQ_ERR_BAD_ARG, "null pointer in batch call");
+    if (nprob == 0)
+        return PQ_OK;
+    std::lock_guard<std::mutex> lock(g_mu);
+    return laplace_batch_locked(nprob, A, a_off, R, C, rows, r_off, cols, c_off, out, o_off,
+                                out_len);
+}
+
+extern "C" int pq_perm_laplace_c128(const double *A, int R, int C, const int32_t *rows,
+                                    const int32_t *cols, double *out, int *out_len)
+{
+    if (!out || !out_len || (R > 0 && C > 0 && !A))
+        return fail(PQ_ERR_BAD_ARG, "null pointer");
+    const int64_t zero = 0;
+    const int32_t r32 = R, c32 = C;
+    int32_t len = 0;
+    const int rc = pq_perm_laplace_batch_c128(1, A, &zero, &r32, &c32, rows, &zero, cols, &zero,
+                                              out, &zero, &len);
+    if (rc)
+        return rc;
+    *out_len = len;
+    return PQ_OK;
+}
+
+extern "C" int pq_perm_laplace_c64(const float *A, int R, int C, const int32_t *rows,
+                                   const int32_t *cols, float *out, int *out_len)
+{
+    if (!out || !out_len || (R > 0 && C > 0 && !A))
+        return fail(PQ_ERR_BAD_ARG, "null pointer");
+    std::vector<double> Ad((size_t)(R > 0 ? R : 0) * (C > 0 ? C : 0) * 2);
+    for (size_t i = 0; i < Ad.size(); i++)
+        Ad[i] = (double)A[i];
+    std::vector<double> o(2 * (size_t)(C > 0 ? C : 1));
+    const int rc = pq_perm_laplace_c128(Ad.data(), R, C, rows, cols, o.data(), out_len);
+    if (rc)
+        return rc;
+    for (int i = 0; i < 2 * *out_len; i++)
+        out[i] = (float)o[i];
+    return PQ_OK;
+}

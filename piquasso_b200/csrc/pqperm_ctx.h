@@ -1,0 +1,74 @@
+// pqperm_ctx.h -- per-device context and error plumbing shared by the host
+// translation units of libpqperm (pqperm_api.cu, pqperm_api_laplace.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pqperm.h"
+#include "pqperm_limits.h"
+
+namespace pqperm {
+
+constexpr int kMaxGrid = 148 * 32 * 2;
+constexpr int kTimingRing = 64;
+constexpr size_t kA2Doubles = (size_t)(kMaxDigits + 1) * kMaxCols * 2;
+
+struct DeviceCtx {
+    int device = -1;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_up = nullptr;   // uploads of the last enqueue have left h_pinned
+    bool up_pending = false;
+    double *d_A2 = nullptr;        // (kMaxDigits+1) x kMaxCols double2
+    double *d_partials = nullptr;  // kMaxGrid x 4
+    double *d_out = nullptr;       // 4 doubles
+    unsigned long long *d_counter = nullptr;  // segment dispenser of the walk kernels
+    uint8_t *d_sched = nullptr;    // kMaxSegLenNary
+    double *d_wtab = nullptr;      // kMaxSegLenNary
+    double *d_binom = nullptr;     // kMaxDigits * 256
+    double *h_pinned = nullptr;    // staging: A2 + out
+    double last_kernel_ms = -1.0;
+    bool ready = false;
+    uint64_t resident_job = 0;     // id of the pq_perm_job whose inputs sit in the buffers
+    cudaEvent_t ring0[kTimingRing], ring1[kTimingRing];  // event pairs around the kernels
+    uint64_t ring_next = 0;
+    // growable scratch of the batched Laplace path
+    void *d_lap[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // prob, A2, partials, out, U, pmf
+    size_t d_lap_cap[6] = {0, 0, 0, 0, 0, 0};
+    void *h_lap[4] = {nullptr, nullptr, nullptr, nullptr}; // unused, unused, out, pmf (pinned)
+    size_t h_lap_cap[4] = {0, 0, 0, 0};
+};
+
+extern std::mutex g_mu;                 // one caller at a time (GIL-held callers anyway)
+extern std::vector<std::unique_ptr<DeviceCtx>> g_ctx;
+extern std::vector<int> g_devices;
+extern std::atomic<int64_t> g_launches;
+
+// Sets the calling thread's pq_last_error() message and returns `code`.
+int fail(int code, const std::string &msg);
+int fail_cuda(cudaError_t e, const char *what);
+
+#define PQ_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess)                                                         \
+            return ::pqperm::fail_cuda(e__, #call);                                     \
+    } while (0)
+
+// Lazily creates the context of `device` (stream, events, fixed buffers) and
+// makes it current.
+int ctx_get(int device, DeviceCtx **out);
+
+// Grow-only device / pinned-host scratch of the batched Laplace path.
+int grow_dev(DeviceCtx *c, int slot, size_t bytes);
+int grow_host(DeviceCtx *c, int slot, size_t bytes);
+
+} // namespace pqperm

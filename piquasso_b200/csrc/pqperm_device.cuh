@@ -43,13 +43,19 @@ struct LapProblem {
     int q;               // low digits walked inside a segment
     int W;               // terms per segment
     int exp2;            // results are scaled by 2^-exp2 (= sum_rows - 1)
+    int nc;              // active columns (the rest of NCP is padding)
+    int tag;             // caller's index (sampler: row of the pmf output)
     uint8_t mult[kMaxDigits];    // r_d
     uint8_t colmult[kMaxCols];   // c_j (1 for padding columns)
+    uint16_t colmode[kMaxCols];  // gather mode: column of U feeding compact column j
+    uint16_t rowmode[kMaxDigits + 1];  // gather mode: row of U of the pinned row / of digit d-1
 };
 
 struct LapParams {
     const LapProblem *prob;
-    const double2 *A2;   // packed matrices
+    const double2 *U;    // gather mode (sampler): ldu x ldu matrix every problem is a minor of
+    int ldu;
+    const double2 *A2;   // packed mode: per-problem matrices
     double2 *partials;   // [total CTAs][NCP + 1]
     double2 *out;        // [nprob][NCP + 1]: per compact column, then the full product
     int nprob;

@@ -71,6 +71,13 @@ cudaError_t launch_laplace_reduce(const LapParams &P, int ncp1, cudaStream_t str
     laplace_reduce_kernel<<<(P.nprob + 3) / 4, 128, 0, stream>>>(P, ncp1);
     return cudaGetLastError();
 }
+
+cudaError_t launch_sampler_pmf(const LapParams &P, int ncp1, const double2 *U, int d,
+                               double *pmf, cudaStream_t stream)
+{
+    sampler_pmf_kernel<<<P.nprob, 128, 0, stream>>>(P, ncp1, U, d, pmf);
+    return cudaGetLastError();
+}
 #endif
 
 } // namespace pqperm

@@ -57,10 +57,28 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
     const LapProblem &Q = P.prob[s_prob];
     const int D = Q.D, q = Q.q, W = Q.W;
     {
-        const double2 *src = P.A2 + Q.a_off;
         const int nelem = (D + 1) * NCP;
-        for (int i = threadIdx.x; i < nelem; i += NT)
-            smA[i] = src[i];
+        if (P.U) {
+            // gather this problem's minor straight from the shared matrix: row 0 =
+            // pinned row, rows 1..D doubled (src/permanent_laplace.cpp:100-102);
+            // padding columns are (1, 0, 0, ...) so that their s_j == 1
+            for (int i = threadIdx.x; i < nelem; i += NT) {
+                const int r = i / NCP, j = i - r * NCP;
+                double2 v = make_double2(r == 0 ? 1.0 : 0.0, 0.0);
+                if (j < Q.nc) {
+                    v = P.U[(size_t)Q.rowmode[r] * P.ldu + Q.colmode[j]];
+                    if (r > 0) {
+                        v.x *= 2.0;
+                        v.y *= 2.0;
+                    }
+                }
+                smA[i] = v;
+            }
+        } else {
+            const double2 *src = P.A2 + Q.a_off;
+            for (int i = threadIdx.x; i < nelem; i += NT)
+                smA[i] = src[i];
+        }
         // step table of the low counter: digit moved on the step into m, and
         // (-1)^m prod_{d<q} C(r_d, c_d(m))   (cf. pqperm_plan.cpp)
         for (int m = threadIdx.x; m < W; m += NT) {
@@ -294,6 +312,33 @@ static __global__ void __launch_bounds__(128) laplace_reduce_kernel(const LapPar
             im += v.y;
         }
         P.out[(size_t)prob * ncp1 + k] = make_double2(re * scale, im * scale);
+    }
+}
+
+// Sampler epilogue (piquasso/_simulators/passive/sampling.py:736-747 of the
+// reference): pmf[m] = | sum_j in_j * partial_j * U[m, nz_j] |^2 for the d output
+// modes, from the Laplace results still in device memory.  One CTA per problem.
+static __global__ void __launch_bounds__(128) sampler_pmf_kernel(const LapParams P, int ncp1,
+                                                                 const double2 *U, int d,
+                                                                 double *pmf)
+{
+    const LapProblem &Q = P.prob[blockIdx.x];
+    __shared__ double2 w[kMaxCols];
+    for (int k = threadIdx.x; k < Q.nc; k += 128) {
+        const double2 v = P.out[(size_t)blockIdx.x * ncp1 + k];
+        const double c = (double)Q.colmult[k];
+        w[k] = make_double2(c * v.x, c * v.y);
+    }
+    __syncthreads();
+    for (int m = threadIdx.x; m < d; m += 128) {
+        double ar = 0.0, ai = 0.0;
+        const double2 *row = U + (size_t)m * d;
+        for (int k = 0; k < Q.nc; k++) {
+            const double2 u = row[Q.colmode[k]];
+            ar += u.x * w[k].x - u.y * w[k].y;
+            ai += u.x * w[k].y + u.y * w[k].x;
+        }
+        pmf[(size_t)blockIdx.x * d + m] = ar * ar + ai * ai;
     }
 }
 

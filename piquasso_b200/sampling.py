@@ -89,6 +89,34 @@ def _to_first_quantized(occupation):
     return np.array(out, dtype=int)
 
 
+def sampler_pmf(interferometer, out_occ, in_occ):
+    """Unnormalised pmf rows of one photon step for many shots at once
+    (``pq_sampler_pmf_c128``): row s is ``_calculate_pmf(in_occ[s], out_occ[s],
+    permanent_laplace, interferometer)`` of the reference before normalisation
+    (``piquasso/_simulators/passive/sampling.py:723-749``)."""
+    lib = _lib.load()
+    U = np.ascontiguousarray(interferometer, dtype=np.complex128)
+    d = U.shape[0]
+    if U.shape != (d, d):
+        raise ValueError("interferometer must be square")
+    oo = np.ascontiguousarray(out_occ, dtype=np.int32).reshape(-1, d)
+    io = np.ascontiguousarray(in_occ, dtype=np.int32).reshape(-1, d)
+    if oo.shape != io.shape:
+        raise ValueError("out_occ and in_occ must have the same shape")
+    pmf = np.empty(oo.shape, dtype=np.float64)
+    rc = lib.pq_sampler_pmf_c128(
+        U.ctypes.data_as(_lib.c_double_p), d, oo.shape[0],
+        oo.ctypes.data_as(_lib.c_int32_p), io.ctypes.data_as(_lib.c_int32_p),
+        pmf.ctypes.data_as(_lib.c_double_p))
+    if rc in (_lib.PQ_ERR_BAD_ARG, _lib.PQ_ERR_TOO_LARGE):
+        raise ValueError(_lib.last_error())
+    _lib.check(rc)
+    TIMERS["  of which GPU kernels (CUDA events)"] = (
+        TIMERS.get("  of which GPU kernels (CUDA events)", 0.0)
+        + max(lib.pq_last_kernel_ms(0), 0.0) * 1e-3)
+    return pmf
+
+
 def generate_samples(input, shots, interferometer, seed_sequence, reject_condition=None,
                      batch_shots=None):
     """Clifford & Clifford algorithm B, all shots in lock step.
@@ -96,15 +124,26 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
     Restates ``_generate_samples`` / ``_generate_sample`` / ``_calculate_pmf``
     (``piquasso/_simulators/passive/sampling.py:149-236, 723-753``) with the
     loops interchanged: outer loop over the n photons, inner (batched) loop over
-    shots.  Shot ``idx`` owns ``np.random.default_rng(seed_sequence + idx)`` and
-    draws ``choice(len(to_shrink))`` then ``choice(arange(d), p=pmf)`` per photon
-    exactly as the reference does, so the returned tuples are identical.
+    shots.  Per photon step ONE library call (``pq_sampler_pmf_c128``) filters
+    the zeros, walks all shots' Laplace problems on the GPU and assembles the
+    pmf rows on the device.
+
+    Host RNG order is the reference's: shot ``idx`` owns
+    ``np.random.default_rng(seed_sequence + idx)`` and per photon draws
+    ``choice(len(to_shrink))`` and then ``choice(arange(d), p=pmf)``.  The two
+    draws are issued here as ``integers(0, len)`` and ``random()`` +
+    ``cdf.searchsorted(u, side="right")``, which is what ``Generator.choice``
+    does internally and consumes the bit stream identically
+    (``tests/test_host.py::test_numpy_choice_equivalences`` pins that), so the
+    returned tuples are identical to the reference's for the same seed.
 
     ``reject_condition`` (uniform losses, ``simulation_steps.py:350-360``) is a
     state-independent callable the reference evaluates once per photon per shot
     in shot-major order, possibly drawing from a shared generator; it is
     therefore evaluated up front in that same order.
     """
+    import time
+
     input = np.asarray(input, dtype=int)
     U = np.ascontiguousarray(interferometer, dtype=np.complex128)
     d = len(input)
@@ -118,45 +157,45 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
         rejected = np.array([[bool(reject_condition()) for _ in range(n)]
                              for _ in range(shots)], dtype=bool).reshape(shots, n)
     samples_all = []
+    cols = np.arange(max(n, 1))
     for start in range(0, shots, max(1, batch_shots)):
         stop = min(shots, start + max(1, batch_shots))
         nb = stop - start
         rngs = [np.random.default_rng(seed=seed_sequence + idx) for idx in range(start, stop)]
-        sample = np.zeros((nb, d), dtype=int)
-        current_input = np.zeros((nb, d), dtype=int)
-        to_shrink = [np.copy(first_quantized) for _ in range(nb)]
-        arange_d = np.arange(d)
-        import time
+        sample = np.zeros((nb, d), dtype=np.int32)
+        current_input = np.zeros((nb, d), dtype=np.int32)
+        # to_shrink of every shot as rows of one array, `remaining` entries valid
+        shrink = np.tile(first_quantized, (nb, 1)) if n else np.zeros((nb, 0), dtype=int)
+        remaining = np.full(nb, n, dtype=np.int64)
         for photon in range(n):
             t0 = time.perf_counter()
-            mats, rws, cls, nz = [], [], [], []
-            live = [s for s in range(nb) if not rejected[start + s, photon]]
-            for s in live:
-                # _grow_current_input (sampling.py:197-205)
-                ridx = rngs[s].choice(len(to_shrink[s]))
-                mode = to_shrink[s][ridx]
-                current_input[s, mode] += 1
-                to_shrink[s] = np.delete(to_shrink[s], ridx)
-                # _filter_zeros (sampling.py:711-720)
-                in_nz = current_input[s] > 0
-                out_nz = sample[s] > 0
-                mats.append(U[np.ix_(out_nz, in_nz)])
-                rws.append(sample[s][out_nz])
-                cls.append(current_input[s][in_nz])
-                nz.append(arange_d[in_nz])
-            _tick("host: grow input + filter", t0)
+            live = np.flatnonzero(~rejected[start:stop, photon])
+            if live.size == 0:
+                continue
+            # _grow_current_input (sampling.py:197-205): rng.choice(len(to_shrink)),
+            # take that mode, np.delete it (later entries shift left)
+            ridx = np.fromiter((rngs[s].integers(0, remaining[s]) for s in live),
+                               dtype=np.int64, count=live.size)
+            modes = shrink[live, ridx]
+            current_input[live, modes] += 1
+            if n > 1:
+                shifted = np.where(cols[None, : n - 1] >= ridx[:, None],
+                                   shrink[live, 1:], shrink[live, : n - 1])
+                shrink[live, : n - 1] = shifted
+            remaining[live] -= 1
+            _tick("host: grow input", t0)
             t0 = time.perf_counter()
-            partials = permanent_laplace_batch(mats, rws, cls)
-            _tick("permanent_laplace_batch (pack + plan + GPU)", t0)
+            pmf = sampler_pmf(U, sample[live], current_input[live])
+            _tick("pq_sampler_pmf_c128 (filter + plan + GPU walk + pmf)", t0)
             t0 = time.perf_counter()
-            for i, s in enumerate(live):
-                # _calculate_pmf (sampling.py:736-749): pmf[m] = |sum_j in_j p_j U[m, nz_j]|^2
-                weights = current_input[s][nz[i]] * partials[i]
-                amp = U[:, nz[i]] @ weights
-                pmf = np.abs(amp) ** 2
-                pmf = pmf / pmf.sum()
-                index = rngs[s].choice(arange_d, p=pmf)
-                sample[s, index] += 1
-            _tick("host: pmf + rng.choice", t0)
+            # _calculate_pmf normalisation (sequential sum) and _sample_from_pmf:
+            # Generator.choice(a, p=p) = cdf.searchsorted(random(), side="right")
+            p = pmf / np.cumsum(pmf, axis=1)[:, -1:]
+            cdf = np.cumsum(p, axis=1)
+            cdf /= cdf[:, -1:]
+            u = np.fromiter((rngs[s].random() for s in live), dtype=np.float64, count=live.size)
+            index = (cdf <= u[:, None]).sum(axis=1)
+            sample[live, index] += 1
+            _tick("host: normalise + draw", t0)
         samples_all.extend(tuple(int(x) for x in row) for row in sample)
     return samples_all

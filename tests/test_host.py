@@ -168,3 +168,22 @@ def test_pybind_module_surface():
     assert out.shape == (1,) and out[0] == 1
     with pytest.raises(RuntimeError):
         native.permanent(np.eye(2, dtype=complex), [1, 1], [1, 0])
+
+
+def test_numpy_choice_equivalences():
+    """The lock-step sampler issues Generator.choice's two forms as integers() and
+    random() + searchsorted; both must consume the bit stream exactly like choice
+    (numpy/random/_generator.pyx) or the samples would differ from the reference's."""
+    for seed in range(200):
+        a = np.random.default_rng(seed)
+        b = np.random.default_rng(seed)
+        for m in (25, 24, 7, 3, 2, 1, 13, 100):
+            assert a.choice(m) == b.integers(0, m)
+        p = np.random.default_rng(seed + 1000).random(50)
+        p /= p.sum()
+        x = a.choice(np.arange(50), p=p)
+        cdf = p.cumsum()
+        cdf /= cdf[-1]
+        u = b.random()
+        assert x == cdf.searchsorted(u, side="right") == (cdf <= u).sum()
+        assert a.random() == b.random()
