@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
 {
     constexpr int NCP = NCL * S;
     constexpr int NT = kLapThreads;
+    constexpr int CH = NCL >= 10 ? 3 : (NCL >= 5 ? 2 : 1); // independent chains per lane
+    constexpr int CLEN = (NCL + CH - 1) / CH;              // longest chunk
     extern __shared__ double2 smA[];              // (D+1) x NCP
     __shared__ double s_wtab[kLapMaxSegLen];
     __shared__ uint8_t s_sched[kLapMaxSegLen];
@@ -189,70 +191,125 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
             }
             const double w = factor * s_wtab[m];
 
-            // suffix products of this lane's columns: sufr[j] = prod_{k >= j} s_k^{c_k}
-            double sufr[NCL + 1], sufi[NCL + 1];
-            sufr[NCL] = 1.0;
-            sufi[NCL] = 0.0;
+            // ---- all C leave-one-out products of this term -------------------
+            // The lane's columns are cut into CH chunks whose suffix / prefix
+            // chains are independent (interleaved below so that the FP64 pipe
+            // sees CH chains at once); the product of everything OUTSIDE a chunk
+            // (other chunks, other lanes) is folded into the start value of the
+            // chunk's prefix chain, so no multiply is added per column:
+            //   P_j = start_c * prod_{k<j in chunk} s_k^{c_k} * s_j^{c_j-1} * suf[j+1]
+            double sufr[NCL], sufi[NCL]; // suf[j] = prod_{k >= j, k in chunk(j)} s_k^{c_k}
 #pragma unroll
-            for (int j = NCL - 1; j >= 0; j--) {
-                double tr = sufr[j + 1], ti = sufi[j + 1];
-                if (UNITCOLS) {
-                    if (j == NCL - 1) {
-                        tr = sr[j];
-                        ti = si[j];
-                    } else {
-                        cmul(tr, ti, sr[j], si[j]);
+            for (int i = CLEN - 1; i >= 0; i--) {
+#pragma unroll
+                for (int c = 0; c < CH; c++) {
+                    const int j0 = (NCL * c) / CH, j1 = (NCL * (c + 1)) / CH;
+                    const int j = j0 + i;
+                    if (j < j1) {
+                        double tr = sr[j], ti = si[j];
+                        if (!UNITCOLS) {
+                            const int cm = Q.colmult[j * S + h];
+                            for (int k = 1; k < cm; k++)
+                                cmul(tr, ti, sr[j], si[j]);
+                        }
+                        if (j + 1 < j1)
+                            cmul(tr, ti, sufr[j + 1], sufi[j + 1]);
+                        sufr[j] = tr;
+                        sufi[j] = ti;
                     }
-                } else {
-                    const int c = Q.colmult[j * S + h];
-                    for (int k = 0; k < c; k++)
-                        cmul(tr, ti, sr[j], si[j]);
                 }
-                sufr[j] = tr;
-                sufi[j] = ti;
             }
-            // product of the columns owned by the other lanes of the group
-            double prer = 1.0, prei = 0.0;
+            // chunk totals -> lane total -> product over the other lanes
+            double lr = sufr[0], li = sufi[0];
+#pragma unroll
+            for (int c = 1; c < CH; c++)
+                cmul(lr, li, sufr[(NCL * c) / CH], sufi[(NCL * c) / CH]);
+            double olr = 1.0, oli = 0.0; // other lanes (S > 1 only)
             if (S > 1) {
-                bool first = true;
 #pragma unroll
                 for (int x = 1; x < S; x++) {
-                    const double orr = __shfl_xor_sync(0xffffffffu, sufr[0], x);
-                    const double oi = __shfl_xor_sync(0xffffffffu, sufi[0], x);
-                    if (first) {
-                        prer = orr;
-                        prei = oi;
-                        first = false;
+                    const double orr = __shfl_xor_sync(0xffffffffu, lr, x);
+                    const double oi = __shfl_xor_sync(0xffffffffu, li, x);
+                    if (x == 1) {
+                        olr = orr;
+                        oli = oi;
                     } else {
-                        cmul(prer, prei, orr, oi);
+                        cmul(olr, oli, orr, oi);
                     }
                 }
             }
-            // prefix pass: P_j = pre * s_j^{c_j - 1} * suf_{j+1}
+            // start value of every chunk's prefix chain: everything outside the chunk
+            double prer[CH], prei[CH];
+            {
+                double lor = olr, loi = oli; // other lanes * chunks before c
+                bool have = S > 1;
 #pragma unroll
-            for (int j = 0; j < NCL; j++) {
-                double pr = prer, pi = prei;
-                if (UNITCOLS) {
-                    if (j + 1 < NCL)
-                        cmul(pr, pi, sufr[j + 1], sufi[j + 1]);
-                    accr[j] = __fma_rn(w, pr, accr[j]);
-                    acci[j] = __fma_rn(w, pi, acci[j]);
-                    cmul(prer, prei, sr[j], si[j]);
-                } else {
-                    const int c = Q.colmult[j * S + h];
-                    for (int k = 0; k < c - 1; k++)
-                        cmul(pr, pi, sr[j], si[j]);
-                    double fr = pr, fi = pi; // pre * s_j^{c_j - 1}
-                    cmul(pr, pi, sufr[j + 1], sufi[j + 1]);
-                    accr[j] = __fma_rn(w, pr, accr[j]);
-                    acci[j] = __fma_rn(w, pi, acci[j]);
-                    cmul(fr, fi, sr[j], si[j]);
-                    prer = fr;
-                    prei = fi;
+                for (int c = 0; c < CH; c++) {
+                    double hr = 1.0, hi2 = 0.0; // chunks after c
+                    bool hhave = false;
+#pragma unroll
+                    for (int c2 = CH - 1; c2 > c; c2--) {
+                        const int f = (NCL * c2) / CH;
+                        if (!hhave) {
+                            hr = sufr[f];
+                            hi2 = sufi[f];
+                            hhave = true;
+                        } else {
+                            cmul(hr, hi2, sufr[f], sufi[f]);
+                        }
+                    }
+                    if (have && hhave) {
+                        prer[c] = lor;
+                        prei[c] = loi;
+                        cmul(prer[c], prei[c], hr, hi2);
+                    } else if (have) {
+                        prer[c] = lor;
+                        prei[c] = loi;
+                    } else {
+                        prer[c] = hr; // (1, 0) when there is nothing outside
+                        prei[c] = hi2;
+                    }
+                    const int f = (NCL * c) / CH;
+                    if (!have) {
+                        lor = sufr[f];
+                        loi = sufi[f];
+                        have = true;
+                    } else {
+                        cmul(lor, loi, sufr[f], sufi[f]);
+                    }
+                }
+                // lor now holds the product of ALL columns: what a c_l = 0 column gets
+                fullr = __fma_rn(w, lor, fullr);
+                fulli = __fma_rn(w, loi, fulli);
+            }
+            // prefix chains, interleaved over the chunks
+#pragma unroll
+            for (int i = 0; i < CLEN; i++) {
+#pragma unroll
+                for (int c = 0; c < CH; c++) {
+                    const int j0 = (NCL * c) / CH, j1 = (NCL * (c + 1)) / CH;
+                    const int j = j0 + i;
+                    if (j < j1) {
+                        double pr = prer[c], pi = prei[c];
+                        int cm = 1;
+                        if (!UNITCOLS) {
+                            cm = Q.colmult[j * S + h];
+                            for (int k = 1; k < cm; k++)
+                                cmul(pr, pi, sr[j], si[j]); // pre * s_j^{c_j - 1}
+                        }
+                        if (j + 1 < j1) {
+                            // next start of the chain: pre * s_j^{c_j}
+                            double nr = pr, ni = pi;
+                            cmul(nr, ni, sr[j], si[j]);
+                            prer[c] = nr;
+                            prei[c] = ni;
+                            cmul(pr, pi, sufr[j + 1], sufi[j + 1]);
+                        }
+                        accr[j] = __fma_rn(w, pr, accr[j]);
+                        acci[j] = __fma_rn(w, pi, acci[j]);
+                    }
                 }
             }
-            fullr = __fma_rn(w, prer, fullr); // all columns: what a c_l = 0 column receives
-            fulli = __fma_rn(w, prei, fulli);
         }
     }
 

@@ -316,3 +316,80 @@ def test_pybind_dropin_module():
         native.permanent(np.eye(2, dtype=complex), [1, 1], [1, 0])
     with pytest.raises(TypeError):  # no forcecast: complex128 -> complex64 is refused, and
         native.permanent("not a matrix", [1], [1])  # junk matches no overload
+
+
+def test_sampler_pmf_rows_match_the_reference_formula():
+    """pq_sampler_pmf_c128 against _calculate_pmf (sampling.py:723-749) evaluated
+    with the oracle's permanent_laplace: zero filtering, early-out, collisions."""
+    from piquasso_b200.sampling import sampler_pmf
+    rng = np.random.default_rng(43)
+    d = 9
+    u = haar(d, 77)
+    outs, ins = [], []
+    for trial in range(40):
+        k = int(rng.integers(1, 8))
+        ins.append(rng.multinomial(k, np.ones(d) / d))
+        outs.append(rng.multinomial(k - 1, np.ones(d) / d) if k > 1 else np.zeros(d, int))
+    got = sampler_pmf(u, np.array(outs), np.array(ins))
+    for s in range(len(outs)):
+        inz, onz = ins[s] > 0, outs[s] > 0
+        part = oracle.permanent_laplace(u[np.ix_(onz, inz)], outs[s][onz], ins[s][inz], precision=1)
+        idx = np.arange(d)[inz]
+        want = np.zeros(d)
+        for m in range(d):
+            amp = sum(ins[s][idx[j]] * part[j] * u[m, idx[j]] for j in range(len(part)))
+            want[m] = abs(amp) ** 2
+        assert np.allclose(got[s], want, rtol=1e-10, atol=1e-15), s
+
+
+def test_sampler_identical_to_sequential_reference_algorithm():
+    """Lock-step sampler == the reference's per-shot loop (sampling.py:208-236)
+    driven by the oracle's permanent_laplace, at the shape of BASELINE config 4
+    scaled down (40 modes, 10 photons)."""
+    from piquasso_b200.sampling import generate_samples
+    d, n, seed = 40, 10, 7
+    u = haar(d, 40)
+    inp = np.array([1] * n + [0] * (d - n))
+    got = generate_samples(inp, 6, u, seed)
+
+    def ref_shot(sd):
+        rng = np.random.default_rng(sd)
+        sample = np.zeros(d, dtype=int)
+        cur = np.zeros(d, dtype=int)
+        shrink = np.repeat(np.arange(d), inp)
+        for _ in range(n):
+            ri = rng.choice(len(shrink))
+            cur[shrink[ri]] += 1
+            shrink = np.delete(shrink, ri)
+            nz, oz = cur > 0, sample > 0
+            part = oracle.permanent_laplace(u[np.ix_(oz, nz)], sample[oz], cur[nz])
+            idx = np.arange(d)[nz]
+            pmf = np.empty(d)
+            norm = 0.0
+            for m in range(d):
+                p = 0.0
+                for j in range(len(part)):
+                    p += cur[idx[j]] * part[j] * u[m, idx[j]]
+                pmf[m] = np.abs(p) ** 2
+                norm += pmf[m]
+            sample[rng.choice(np.arange(d), p=pmf / norm)] += 1
+        return tuple(int(x) for x in sample)
+
+    assert got == [ref_shot(seed + i) for i in range(6)]
+
+
+def test_single_process_multi_device_split(lib):
+    """pq_set_devices: one permanent split over the visible devices of one process."""
+    import ctypes
+    ndev = lib.pq_device_count()
+    if ndev < 2:
+        pytest.skip("needs two devices")
+    a = haar(27, 27)
+    ones = np.ones(27, np.int32)
+    base = complex(permanent(a, ones, ones))
+    ids = (ctypes.c_int32 * ndev)(*range(ndev))
+    try:
+        _lib.check(lib.pq_set_devices(ids, ndev))
+        assert relerr(complex(permanent(a, ones, ones)), base) < 1e-12
+    finally:
+        _lib.check(lib.pq_set_devices((ctypes.c_int32 * 1)(0), 1))
