@@ -10,9 +10,8 @@
 namespace pqperm {
 
 // Parameter block of the single-permanent walks.  Passed by value as a
-// __grid_constant__ so that the small per-digit tables (and, for the binary
-// kernel, the rows of the lowest Gray digits) sit in the constant bank and
-// can be used as immediate-offset operands of FP64 instructions.
+// __grid_constant__ so that the small per-digit tables sit in the constant
+// bank (warp-uniform reads through the uniform datapath).
 struct WalkParams {
     const double2 *A2;     // (D+1) x NC: row 0 = pinned row a_0, rows 1..D = 2*a_d
     const uint8_t *sched;  // [W] digit that moves on the step INTO local index m (n-ary only)

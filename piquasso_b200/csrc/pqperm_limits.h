@@ -12,7 +12,7 @@ constexpr int kMaxLowDigits = 24;       // digits walked inside one segment
 constexpr int kMaxMultiplicity = 254;   // radix r+1 is stored in a byte
 constexpr int kBinMinCols = 8;          // narrowest binary constant-bank kernel
 constexpr int kBinMaxCols = 48;         // widest binary constant-bank kernel
-constexpr int kBinMaxBlockExp = 4;      // kernel 2: at most 2^4 terms per block
+constexpr int kBinMaxBlockExp = 4;      // kernel 2: at most 2^4 terms per block (instantiated for C <= 32)
 // kernel 2: log2 of the terms per block for nc columns (register budget:
 // 4*nc for the row sums + 4 * 2^B for the running products)
 inline int binary_block_exponent(int /*nc*/) { return 3; }  // measured best for 20 <= nc <= 48

@@ -46,24 +46,14 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
     }
     plan.sum_rows = (int)sum_rows;
 
-    const bool empty = (R == 0 || C == 0 || sum_rows == 0 || sum_cols == 0);
-    if (opt.laplace) {
-        // src/permanent_laplace.cpp:52-57: early-out before anything else; the
-        // Laplace entry never compares the two sums.
-        if (empty) {
-            plan.trivial = 1;
-            return PQ_OK;
-        }
-    } else {
-        // src/permanent.cpp:97-108 (the split does not change sum(rows))
-        if (sum_rows != sum_cols) {
-            err = "Number of input and output states should be equal";
-            return PQ_ERR_SUM_MISMATCH;
-        }
-        if (empty) {
-            plan.trivial = 1;
-            return PQ_OK;
-        }
+    // src/permanent.cpp:97-108 (the split does not change sum(rows))
+    if (sum_rows != sum_cols) {
+        err = "Number of input and output states should be equal";
+        return PQ_ERR_SUM_MISMATCH;
+    }
+    if (R == 0 || C == 0 || sum_rows == 0 || sum_cols == 0) {
+        plan.trivial = 1;
+        return PQ_OK;
     }
 
     // src/permanent.cpp:54-64: first index attaining the smallest non-zero
@@ -134,21 +124,18 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
         forced_B = (choice / 10) % 10;
         choice = choice % 10;
     }
-    const bool bin_ok = !opt.laplace && plan.binary && plan.unitcols &&
+    const bool bin_ok = plan.binary && plan.unitcols &&
                         plan.NC >= kBinMinCols && plan.NC <= kBinMaxCols;
     plan.kernel = 1;
     if (bin_ok && choice != 1) {
-        plan.B = forced_B ? forced_B : binary_block_exponent(plan.NC);
+        plan.B = forced_B ? std::min(std::max(forced_B, 2), plan.NC <= 32 ? kBinMaxBlockExp : 3)
+                          : binary_block_exponent(plan.NC);
         // automatic choice: only where the term space is large enough to repay the
         // constant-bank upload; forced (tests, tuning): wherever a block fits
         if (plan.D >= (choice == 2 ? plan.B : kBinMinDigitsAuto))
             plan.kernel = 2;
     }
     plan.NCP = plan.kernel == 2 ? plan.NC : (plan.NC <= 4 ? 4 : (plan.NC + 3) / 4 * 4);
-    if (opt.laplace) {
-        const LapVariant v = laplace_variant(plan.NC);
-        plan.NCP = v.S * v.NCL;
-    }
     plan.colmult.resize(plan.NCP, 1);
 
     // ---- where to cut the digits --------------------------------------------
@@ -156,15 +143,9 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
     const double regs = 4.0 * plan.NCP + 48.0;
     double resident = std::floor(65536.0 / regs / 64.0) * 64.0;
     resident = std::max(64.0, std::min(2048.0, resident)) * opt.num_sms;
-    if (opt.laplace) // S lanes per segment; the batch shares the machine
-        resident = std::max(1.0, resident / laplace_variant(plan.NC).S /
-                                     std::max(1, opt.batch));
-    const double step = opt.laplace ? (2.0 * plan.NCP + 14.0 * plan.M)
-                                    : (2.0 * plan.NCP + 4.0 * plan.M + 2.0);
+    const double step = 2.0 * plan.NCP + 4.0 * plan.M + 2.0;
     const double seed = 2.0 * plan.NCP * (plan.D + 1) + 40.0 * plan.D + 100.0;
-    const int64_t wmax = opt.laplace ? (int64_t)kLapMaxSegLen
-                                     : ((plan.binary && plan.unitcols) ? kMaxSegLenBinary
-                                                                       : kMaxSegLenNary);
+    const int64_t wmax = (plan.binary && plan.unitcols) ? kMaxSegLenBinary : kMaxSegLenNary;
     const int qmin = plan.kernel == 2 ? plan.B : 0;
     int best_q = -1;
     double best_cost = 0.0;
@@ -212,7 +193,7 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
         for (int g = 0; g <= plan.mult[d]; g++)
             plan.binom.push_back(binom_d(plan.mult[d], g));
     }
-    if (!(plan.binary && plan.unitcols) && !opt.laplace) {
+    if (!(plan.binary && plan.unitcols)) {
         // step m-1 -> m of the low counter: which digit moves, and the weight
         // (-1)^m prod_{d<q} C(r_d, c_d(m)) (C(r,g) = C(r,r-g): the reflection
         // of a digit does not change its binomial).

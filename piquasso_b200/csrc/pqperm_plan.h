@@ -54,8 +54,6 @@ struct PlanOptions {
     int kernel_choice = 0;    // 0 auto, 1 generic, 2 binary; 2 + 10*B forces the block exponent
     int64_t seg_len_hint = 0; // 0 auto
     int num_sms = 148;
-    bool laplace = false;     // plan for the Laplace walk (different per-term cost)
-    int batch = 1;            // Laplace: problems sharing the launch
 };
 
 // Builds the plan.  `A` may be null (structure only: no A2).  Returns PQ_OK or

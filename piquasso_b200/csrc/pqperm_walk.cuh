@@ -19,9 +19,8 @@
 
 #include "pqperm_device.cuh"
 
-#ifndef PQ_CHAINS
+// independent product chains of the generic walk for NC register-resident columns
 #define PQ_CHAINS(NC) ((NC) >= 16 ? 4 : ((NC) >= 6 ? 2 : 1))
-#endif
 
 namespace pqperm {
 

@@ -393,3 +393,41 @@ def test_single_process_multi_device_split(lib):
         assert relerr(complex(permanent(a, ones, ones)), base) < 1e-12
     finally:
         _lib.check(lib.pq_set_devices((ctypes.c_int32 * 1)(0), 1))
+
+
+def test_wide_problems_against_the_arbiter():
+    """Widths at the edges of the kernel families: 50-64 active columns (generic
+    walk beyond the binary kernel's 48; Laplace lane split S=4 up to NCL=16)."""
+    rng = np.random.default_rng(47)
+    # permanent: few n-ary rows, many unit columns
+    for rows in ([50], [30, 24], [13, 13, 13, 13], [20, 20, 20, 4]):
+        rows = np.array(rows)
+        n = int(rows.sum())
+        a = rng.normal(size=(len(rows), n)) + 1j * rng.normal(size=(len(rows), n))
+        cols = np.ones(n, int)
+        # high multiplicities cancel catastrophically (sum_g (-1)^g C(r,g) (r+1-2g)^n):
+        # the bar is the reference-style double computation measured against the
+        # long-double arbiter, not 1e-10
+        want = oracle.permanent(a, rows, cols, precision=1)
+        ref_err = relerr(oracle.permanent(a, rows, cols), want)
+        assert relerr(complex(permanent(a, rows, cols)), want) <= max(1e-10, 20 * ref_err), rows
+    # permanent_laplace: NC = 14 (S=2), 30 (S=4), 52, 64 (S=4, NCL=13/16), n-ary rows
+    for nc, rows in ((14, [4, 4, 3, 2]), (30, [6, 6, 6, 6, 5]), (52, [13, 13, 13, 12]),
+                     (64, [21, 21, 21])):
+        rows = np.array(rows)
+        assert rows.sum() == nc - 1
+        a = (rng.normal(size=(len(rows), nc)) + 1j * rng.normal(size=(len(rows), nc))) / 3
+        cols = np.ones(nc, int)
+        want = oracle.permanent_laplace(a, rows, cols, precision=1)
+        ref_err = np.max(np.abs(oracle.permanent_laplace(a, rows, cols) - want) / np.abs(want))
+        got = permanent_laplace(a, rows, cols)
+        assert got.shape == (nc,)
+        assert np.max(np.abs(got - want) / np.abs(want)) <= max(1e-10, 20 * ref_err), nc
+    # column multiplicities on a wide Laplace problem
+    a = (rng.normal(size=(3, 20)) + 1j * rng.normal(size=(3, 20))) / 3
+    cols = np.array([2, 1] * 10)
+    rows = np.array([10, 10, 9])
+    want = oracle.permanent_laplace(a, rows, cols, precision=1)
+    ref_err = np.max(np.abs(oracle.permanent_laplace(a, rows, cols) - want) / np.abs(want))
+    got = permanent_laplace(a, rows, cols)
+    assert np.max(np.abs(got - want) / np.abs(want)) <= max(1e-10, 20 * ref_err)
