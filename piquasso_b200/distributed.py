@@ -97,5 +97,42 @@ def permanent_allgather(matrix, rows, cols, group=None, device_index=None):
     return np.array(np.complex128(finish(total, int(r.sum()))))
 
 
+def generate_samples_sharded(input, shots, interferometer, seed_sequence,
+                             reject_condition=None, group=None):
+    """The lock-step sampler with the SHOTS sharded over the ranks of ``group``.
+
+    Shots are independent (shot ``idx`` owns ``default_rng(seed_sequence + idx)``),
+    so rank g of G simply runs shots ``[shots*g//G, shots*(g+1)//G)`` on its own
+    GPU; there is no exchange step on the data path, only one all-gather of the
+    finished samples at the end.  Every rank returns the full list, identical to
+    the single-GPU (and to the reference's) result.
+
+    ``reject_condition`` is evaluated by every rank for ALL shots in the
+    reference's shot-major order (it may draw from a generator the ranks seeded
+    identically), and each rank keeps its own rows."""
+    import torch.distributed as dist
+
+    from .sampling import generate_samples
+
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    n = int(np.sum(np.asarray(input, dtype=int)))
+    begin, end = (shots * rank) // world, (shots * (rank + 1)) // world
+    rejects = None
+    if reject_condition is not None:
+        table = [[bool(reject_condition()) for _ in range(n)] for _ in range(shots)]
+        flat = iter([x for row in table[begin:end] for x in row])
+        rejects = lambda: next(flat)  # noqa: E731
+    mine = generate_samples(input, end - begin, interferometer, seed_sequence + begin,
+                            reject_condition=rejects)
+    if world == 1:
+        return mine
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine, group=group)
+    return [s for part in gathered for s in part]
+
+
 # the exchange step used to be an all-reduce; keep the old name importable
 permanent_allreduce = permanent_allgather

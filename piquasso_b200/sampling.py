@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["permanent_laplace_batch", "generate_samples"]
+__all__ = ["permanent_laplace_batch", "grad_perm", "sampler_pmf", "generate_samples"]
 
 # wall-clock split of generate_samples (seconds), for tools/sampler_bench.py
 TIMERS = {}
@@ -79,6 +79,43 @@ def permanent_laplace_batch(matrices, rows_list, cols_list):
         raise ValueError(_lib.last_error())
     _lib.check(rc)
     return [out[o_off[b]: o_off[b] + out_len[b]].copy() for b in range(n)]
+
+
+def grad_perm(matrix, rows, cols):
+    """Gradient of the permanent with respect to every matrix element, what the
+    reference's ``grad_perm`` (``src/permanent.cpp:271-300``, used by its JAX
+    VJP) computes with one ``permanent_cpp`` call per element:
+
+        grad[i, j] = rows[i] * cols[j] * perm(A, rows - e_i, cols - e_j)
+
+    Here row i is ONE Laplace problem -- ``permanent_laplace(A, rows - e_i,
+    cols)[j]`` is exactly ``perm(A, rows - e_i, cols - e_j)`` -- so the whole
+    gradient is a single batched call of at most ``len(rows)`` problems.  Entries
+    with ``rows[i] == 0`` or ``cols[j] == 0`` are zero, as in the reference."""
+    a = np.ascontiguousarray(matrix, dtype=np.complex128)
+    r = np.asarray(rows).astype(np.int64)
+    c = np.asarray(cols).astype(np.int64)
+    if a.shape != (len(r), len(c)):
+        raise ValueError("multiplicities do not match the matrix")
+    grad = np.zeros(a.shape, dtype=np.complex128)
+    live = [i for i in range(len(r)) if r[i] > 0]
+    if not live or c.sum() == 0:
+        return grad
+    rws = []
+    for i in live:
+        ri = r.copy()
+        ri[i] -= 1
+        rws.append(ri)
+    parts = permanent_laplace_batch([a] * len(live), rws, [c] * len(live))
+    for i, part in zip(live, parts):
+        if len(part) == len(c):
+            grad[i, :] = r[i] * c * part
+        else:
+            # early-out [1] (all remaining rows empty): perm of the empty minor is 1
+            # for the single photon's column
+            grad[i, :] = r[i] * c * (c > 0) * part[0] * (c.sum() == 1)
+    grad[:, c == 0] = 0.0
+    return grad
 
 
 def _to_first_quantized(occupation):

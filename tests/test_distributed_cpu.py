@@ -72,3 +72,49 @@ def test_two_ranks_gloo_sum_to_the_permanent():
             got = results[rank][i]
             assert abs(got - want) <= 1e-12 * max(abs(want), 1e-3), (i, rank, got, want)
         assert results[0][i] == results[1][i]  # every rank holds the same value
+
+
+def _oracle_sampler_pmf(interferometer, out_occ, in_occ):
+    """Stand-in for pq_sampler_pmf_c128 built on the oracle (CPU ranks)."""
+    u = np.asarray(interferometer)
+    d = u.shape[0]
+    out = np.zeros((len(out_occ), d))
+    for s, (oo, io) in enumerate(zip(np.asarray(out_occ), np.asarray(in_occ))):
+        inz, onz = io > 0, oo > 0
+        part = oracle.permanent_laplace(u[np.ix_(onz, inz)], oo[onz], io[inz])
+        idx = np.arange(d)[inz]
+        for m in range(d):
+            amp = sum(io[idx[j]] * part[j] * u[m, idx[j]] for j in range(len(part)))
+            out[s, m] = abs(amp) ** 2
+    return out
+
+
+def _sampler_worker(rank, world, port, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from piquasso_b200 import distributed, sampling
+    sampling.sampler_pmf = _oracle_sampler_pmf
+    u = haar(6, 3)
+    results[rank] = distributed.generate_samples_sharded([1, 1, 0, 2, 0, 0], 7, u, 11)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sampler_shots_sharded_over_two_ranks():
+    """Shots are sharded with no data-path collective; both ranks end with the
+    single-process sample list (same per-shot seeds)."""
+    from piquasso_b200 import sampling
+    world = 2
+    manager = mp.Manager()
+    results = manager.dict()
+    mp.spawn(_sampler_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    saved = sampling.sampler_pmf
+    sampling.sampler_pmf = _oracle_sampler_pmf
+    try:
+        want = sampling.generate_samples([1, 1, 0, 2, 0, 0], 7, haar(6, 3), 11)
+    finally:
+        sampling.sampler_pmf = saved
+    assert results[0] == want and results[1] == want
+    assert len(want) == 7 and all(sum(s) == 4 for s in want)

@@ -431,3 +431,35 @@ def test_wide_problems_against_the_arbiter():
     ref_err = np.max(np.abs(oracle.permanent_laplace(a, rows, cols) - want) / np.abs(want))
     got = permanent_laplace(a, rows, cols)
     assert np.max(np.abs(got - want) / np.abs(want)) <= max(1e-10, 20 * ref_err)
+
+
+def test_grad_perm_matches_elementwise_permanents():
+    """grad[i,j] = rows[i] cols[j] perm(A, rows-e_i, cols-e_j)  (src/permanent.cpp:271-300)."""
+    from piquasso_b200.sampling import grad_perm
+    rng = np.random.default_rng(53)
+    for trial in range(8):
+        d = int(rng.integers(1, 6))
+        nph = int(rng.integers(1, 7))
+        rows = rng.multinomial(nph, np.ones(d) / d)
+        cols = rng.multinomial(nph, np.ones(d) / d)
+        a = haar(d, 60 + trial)
+        got = grad_perm(a, rows, cols)
+        for i in range(d):
+            for j in range(d):
+                if rows[i] == 0 or cols[j] == 0:
+                    assert got[i, j] == 0
+                    continue
+                r2, c2 = rows.copy(), cols.copy()
+                r2[i] -= 1
+                c2[j] -= 1
+                want = rows[i] * cols[j] * oracle.permanent(a, r2, c2, precision=1)
+                assert close(got[i, j], want, rtol=1e-10, atol=1e-13), (rows, cols, i, j)
+    # finite-difference check of the meaning of "gradient": d perm / d a_ij
+    a = haar(4, 9)
+    ones = np.ones(4, int)
+    g = grad_perm(a, ones, ones)
+    eps = 1e-6
+    b = a.copy()
+    b[1, 2] += eps
+    fd = (oracle.permanent(b, ones, ones) - oracle.permanent(a, ones, ones)) / eps
+    assert abs(g[1, 2] - fd) < 1e-6
