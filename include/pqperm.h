@@ -91,6 +91,18 @@ int pq_perm_laplace_batch_c128(int nprob, const double *A, const int64_t *a_off,
                                int32_t *out_len);
 
 /* ---------------------------------------------------------------------
+ * Many permanents of ONE matrix with different multiplicity vectors in one
+ * call: out[b] = permanent(A, row_mult[b*R ..], col_mult[b*C ..]).  This is
+ * the batched form of connector.permanent(interferometer, cols=input,
+ * rows=output) (piquasso/_simulators/passive/utils.py:131-138,
+ * probabilities.py:26-54) for tables of detection amplitudes: the matrix is
+ * uploaded once and every CTA gathers its own minor.  A sum mismatch in any
+ * problem fails the whole call with PQ_ERR_SUM_MISMATCH.
+ * ------------------------------------------------------------------- */
+int pq_perm_batch_c128(const double *A, int R, int C, int nprob, const int32_t *row_mult,
+                       const int32_t *col_mult, double *out);
+
+/* ---------------------------------------------------------------------
  * One photon step of the Clifford-Clifford sampler for `nshots` independent
  * shots sharing one d x d interferometer U (row-major complex128).  For shot s,
  * with the output occupations placed so far out_occ[s*d .. ] and the input

@@ -62,6 +62,8 @@ SIGNATURES = [
     ("pq_perm_laplace_batch_c128", ctypes.c_int,
      [ctypes.c_int, c_double_p, c_int64_p, c_int32_p, c_int32_p, c_int32_p, c_int64_p,
       c_int32_p, c_int64_p, c_double_p, c_int64_p, c_int32_p]),
+    ("pq_perm_batch_c128", ctypes.c_int,
+     [c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, c_double_p]),
     ("pq_sampler_pmf_c128", ctypes.c_int,
      [c_double_p, ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, c_double_p]),
     ("pq_perm_partial_c128", ctypes.c_int,

@@ -166,6 +166,7 @@ struct Epilogue {
     const double2 *d_U = nullptr; // gather mode / sampler: matrix on the device
     int ldu = 0;
     double *pmf = nullptr;        // sampler: host [nshots][ldu], row = LapProblem.tag
+    bool perm_only = false;       // batched permanents: only the full product
 };
 
 // One bucket = one walk launch + one reduce launch (+ pmf epilogue).  Without
@@ -210,6 +211,7 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
     P.partials = reinterpret_cast<double2 *>(c->d_lap[2]);
     P.out = reinterpret_cast<double2 *>(c->d_lap[3]);
     P.nprob = n;
+    P.perm_only = (epi && epi->perm_only) ? 1 : 0;
     const size_t smem = (size_t)(bk.max_D + 1) * NCP * sizeof(double2);
     PQ_CUDA(cudaEventRecord(c->ev0, st));
     cudaError_t e = launch_laplace(bk.S, bk.NCL, bk.unit, P, total_blocks, smem, st);
@@ -417,7 +419,97 @@ int sampler_pmf_locked(const double *U, int d, int nshots, const int32_t *out_oc
     return PQ_OK;
 }
 
+// Many permanents of minors (with multiplicities) of one matrix: the batched
+// form of connector.permanent(interferometer, cols=input, rows=output)
+// (piquasso/_simulators/passive/utils.py:131-138) for probability tables.
+int perm_batch_locked(const double *U, int R, int C, int nprob, const int32_t *row_mult,
+                      const int32_t *col_mult, double *out)
+{
+    std::string err;
+    LapShape sh;
+    g_buckets.reset();
+    bool any = false;
+    for (int b = 0; b < nprob; b++) {
+        const int32_t *rw = row_mult + (size_t)b * R, *cl = col_mult + (size_t)b * C;
+        int rc = lap_shape(R, C, rw, cl, sh, err);
+        if (rc)
+            return fail(rc, err);
+        long long sr = 0, sc = 0;
+        for (int i = 0; i < R; i++)
+            sr += rw[i];
+        for (int j = 0; j < C; j++)
+            sc += cl[j];
+        if (sr != sc) // src/permanent.cpp:97-104
+            return fail(PQ_ERR_SUM_MISMATCH,
+                        "Number of input and output states should be equal (problem " +
+                            std::to_string(b) + ")");
+        if (sh.trivial) { // src/permanent.cpp:106-108
+            out[2 * (size_t)b] = 1.0;
+            out[2 * (size_t)b + 1] = 0.0;
+            continue;
+        }
+        const LapVariant v = laplace_variant(sh.NC);
+        Bucket &bk = g_buckets.get(v, sh.unit);
+        LapProblem q;
+        lap_fill(sh, v.S * v.NCL, q);
+        q.tag = b;
+        q.rowmode[0] = (uint16_t)sh.pinned;
+        for (int k = 0; k < sh.D; k++)
+            q.rowmode[k + 1] = (uint16_t)sh.src_row[k];
+        for (int k = 0; k < sh.NC; k++)
+            q.colmode[k] = (uint16_t)sh.src_col[k];
+        bk.max_D = std::max(bk.max_D, sh.D);
+        bk.probs.push_back(q);
+        any = true;
+    }
+    if (!any)
+        return PQ_OK;
+    DeviceCtx *c = nullptr;
+    int rc = ctx_get(g_devices[0], &c);
+    if (rc)
+        return rc;
+    // gather mode needs a square leading dimension only for addressing: ldu = C
+    const size_t ubytes = (size_t)R * C * sizeof(double2);
+    if ((rc = grow_dev(c, 4, ubytes)))
+        return rc;
+    PQ_CUDA(cudaMemcpyAsync(c->d_lap[4], U, ubytes, cudaMemcpyHostToDevice, c->stream));
+    Epilogue epi;
+    epi.d_U = reinterpret_cast<const double2 *>(c->d_lap[4]);
+    epi.ldu = C;
+    epi.perm_only = true;
+    c->last_kernel_ms = -1.0;
+    for (Bucket &bk : g_buckets.b) {
+        if (bk.probs.empty())
+            continue;
+        rc = run_bucket(c, bk, &epi);
+        if (rc)
+            return rc;
+        const int ncp1 = bk.S * bk.NCL + 1;
+        const double *ho = reinterpret_cast<const double *>(c->h_lap[2]);
+        for (size_t i = 0; i < bk.probs.size(); i++) {
+            const int b = bk.probs[i].tag;
+            out[2 * (size_t)b] = ho[(i * ncp1 + (ncp1 - 1)) * 2];
+            out[2 * (size_t)b + 1] = ho[(i * ncp1 + (ncp1 - 1)) * 2 + 1];
+        }
+    }
+    return PQ_OK;
+}
+
 } // namespace
+
+extern "C" int pq_perm_batch_c128(const double *A, int R, int C, int nprob,
+                                  const int32_t *row_mult, const int32_t *col_mult,
+                                  double *out)
+{
+    if (R < 0 || C < 0 || R > 65535 || C > 65535 || nprob < 0 ||
+        (nprob > 0 && (!out || (R > 0 && !row_mult) || (C > 0 && !col_mult))) ||
+        (R > 0 && C > 0 && !A))
+        return fail(PQ_ERR_BAD_ARG, "bad batch arguments");
+    if (nprob == 0)
+        return PQ_OK;
+    std::lock_guard<std::mutex> lock(g_mu);
+    return perm_batch_locked(A, R, C, nprob, row_mult, col_mult, out);
+}
 
 extern "C" int pq_sampler_pmf_c128(const double *U, int d, int nshots, const int32_t *out_occ,
                                    const int32_t *in_occ, double *pmf)

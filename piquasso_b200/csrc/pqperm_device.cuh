@@ -55,6 +55,7 @@ struct LapParams {
     const double2 *U;    // gather mode (sampler): ldu x ldu matrix every problem is a minor of
     int ldu;
     const double2 *A2;   // packed mode: per-problem matrices
+    int perm_only;       // 1: only the full product is wanted (batched permanents)
     double2 *partials;   // [total CTAs][NCP + 1]
     double2 *out;        // [nprob][NCP + 1]: per compact column, then the full product
     int nprob;

@@ -238,6 +238,14 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                     }
                 }
             }
+            if (P.perm_only) {
+                // batched permanents: the product of ALL columns is the term
+                if (S > 1)
+                    cmul(lr, li, olr, oli);
+                fullr = __fma_rn(w, lr, fullr);
+                fulli = __fma_rn(w, li, fulli);
+                continue;
+            }
             // start value of every chunk's prefix chain: everything outside the chunk
             double prer[CH], prei[CH];
             {

@@ -17,7 +17,8 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["permanent_laplace_batch", "grad_perm", "sampler_pmf", "generate_samples"]
+__all__ = ["permanent_laplace_batch", "permanent_batch", "detection_probabilities",
+           "grad_perm", "sampler_pmf", "generate_samples"]
 
 # wall-clock split of generate_samples (seconds), for tools/sampler_bench.py
 TIMERS = {}
@@ -79,6 +80,48 @@ def permanent_laplace_batch(matrices, rows_list, cols_list):
         raise ValueError(_lib.last_error())
     _lib.check(rc)
     return [out[o_off[b]: o_off[b] + out_len[b]].copy() for b in range(n)]
+
+
+def permanent_batch(matrix, rows_batch, cols_batch):
+    """``[permanent(matrix, r, c) for r, c in zip(rows_batch, cols_batch)]`` in one
+    call (``pq_perm_batch_c128``): one matrix, many multiplicity vectors.
+    ``rows_batch`` is (B, R), ``cols_batch`` (B, C) or a single (C,) vector that
+    is broadcast.  Returns a complex128 array of length B."""
+    lib = _lib.load()
+    a = np.ascontiguousarray(matrix, dtype=np.complex128)
+    if a.ndim != 2:
+        raise ValueError("matrix must be 2-dimensional")
+    R, C = a.shape
+    rb = np.ascontiguousarray(np.asarray(rows_batch).astype(np.int32, casting="unsafe")).reshape(-1, R)
+    cb = np.asarray(cols_batch).astype(np.int32, casting="unsafe")
+    if cb.ndim == 1:
+        cb = np.broadcast_to(cb, (rb.shape[0], C))
+    cb = np.ascontiguousarray(cb).reshape(-1, C)
+    if cb.shape[0] != rb.shape[0]:
+        raise ValueError("rows_batch and cols_batch describe different numbers of problems")
+    out = np.zeros(rb.shape[0], dtype=np.complex128)
+    rc = lib.pq_perm_batch_c128(
+        a.ctypes.data_as(_lib.c_double_p), R, C, rb.shape[0],
+        rb.ctypes.data_as(_lib.c_int32_p), cb.ctypes.data_as(_lib.c_int32_p),
+        out.ctypes.data_as(_lib.c_double_p))
+    if rc in (_lib.PQ_ERR_BAD_ARG, _lib.PQ_ERR_TOO_LARGE):
+        raise ValueError(_lib.last_error())
+    _lib.check(rc)
+    return out
+
+
+def detection_probabilities(interferometer, input, outputs):
+    """Particle-detection probabilities of many output occupations for one input:
+    ``|permanent(U, rows=output, cols=input)|^2 / (prod output! * prod input!)``
+    (``piquasso/_simulators/passive/probabilities.py:26-54`` and
+    ``utils.py:131-138`` of the reference), all outputs in one batched call."""
+    from scipy.special import factorial
+
+    outputs = np.atleast_2d(np.asarray(outputs, dtype=int))
+    input = np.asarray(input, dtype=int)
+    amps = permanent_batch(interferometer, outputs, input)
+    norm = np.prod(factorial(outputs), axis=1) * np.prod(factorial(input))
+    return np.abs(amps) ** 2 / norm
 
 
 def grad_perm(matrix, rows, cols):

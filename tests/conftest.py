@@ -56,6 +56,19 @@ def relerr(a, b):
     return abs(a - b) / max(abs(b), 1e-300)
 
 
+def _ensure_built():
+    """The .so files are git-ignored build products; a checkout that has not run
+    __graft_entry__.build() yet gets them built once (nvcc / gcc, no GPU needed)."""
+    from piquasso_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from piquasso_b200 import build
+        build.build()
+        build.build_pybind()
+
+
+_ensure_built()
+
+
 @pytest.fixture(scope="session")
 def lib():
     from piquasso_b200 import _lib

@@ -463,3 +463,32 @@ def test_grad_perm_matches_elementwise_permanents():
     b[1, 2] += eps
     fd = (oracle.permanent(b, ones, ones) - oracle.permanent(a, ones, ones)) / eps
     assert abs(g[1, 2] - fd) < 1e-6
+
+
+def test_permanent_batch_and_detection_probabilities():
+    """One interferometer, many occupation vectors in one call (probability
+    tables; the reference loops connector.permanent, passive/utils.py:131-138)."""
+    import itertools
+    from piquasso_b200.sampling import detection_probabilities, permanent_batch
+    rng = np.random.default_rng(59)
+    d = 7
+    u = haar(d, 21)
+    rows, cols = [], []
+    for trial in range(64):
+        n = int(rng.integers(0, 7))
+        rows.append(rng.multinomial(n, np.ones(d) / d))
+        cols.append(rng.multinomial(n, np.ones(d) / d))
+    got = permanent_batch(u, np.array(rows), np.array(cols))
+    for b in range(len(rows)):
+        want = oracle.permanent(u, rows[b], cols[b], precision=1)
+        assert close(got[b], want, rtol=1e-10, atol=1e-14), (rows[b], cols[b])
+    # a full probability table: 3 photons in 5 modes sums to one
+    d = 5
+    u = haar(d, 5)
+    inp = np.array([1, 1, 0, 1, 0])
+    outs = [o for o in itertools.product(range(4), repeat=d) if sum(o) == 3]
+    p = detection_probabilities(u, inp, outs)
+    assert len(outs) == 35 and abs(p.sum() - 1.0) < 1e-12
+    # golden values of the reference's tests (tests/_simulators/passive/test_preparations.py:231-282)
+    with pytest.raises(RuntimeError):
+        permanent_batch(u, [[1, 0, 0, 0, 0]], [[1, 1, 0, 0, 0]])
