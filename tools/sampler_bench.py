@@ -19,6 +19,33 @@ print(f"{shots} shots, {d} modes, {n} photons: {dt:.2f} s  ({dt/shots*1e3:.2f} m
 for k, v in sampling.TIMERS.items():
     print(f"   {k}: {v:.3f} s")
 print("first samples:", samples[:2])
+if "--account" in sys.argv:
+    # Gray-code terms actually walked: replay the shots' occupations on the host
+    import numpy as np
+    terms = 0.0; flops = 0.0
+    for smp_i, smp in enumerate(samples[: min(shots, 500)]):
+        # the order in which photons were placed is not recorded; the term count of
+        # step k only needs the multiset of occupied output modes after k-1 photons,
+        # which we re-draw here with the same generator the sampler used
+        rng = np.random.default_rng(123 + smp_i)
+        out = np.zeros(d, dtype=int); cur = np.zeros(d, dtype=int); shrink = np.repeat(np.arange(d), inp)
+        U_ = U
+        for k in range(1, n + 1):
+            ri = rng.integers(0, len(shrink)); cur[shrink[ri]] += 1; shrink = np.delete(shrink, ri)
+            rows = out[out > 0].copy()
+            if rows.size:
+                rows[np.argmin(rows)] -= 1
+                t = float(np.prod(rows + 1))
+                terms += t; flops += t * 22 * k
+            pmf = sampling.sampler_pmf(U_, out[None, :], cur[None, :])[0]
+            p = pmf / np.cumsum(pmf)[-1]; cdf = np.cumsum(p); cdf /= cdf[-1]
+            out[(cdf <= rng.random()).sum()] += 1
+        assert tuple(out) == smp
+    scale = shots / min(shots, 500)
+    gpu_s = sampling.TIMERS.get("  of which GPU kernels (CUDA events)", 0.0)
+    print(f"Gray-code terms walked (extrapolated from {min(shots,500)} shots): {terms*scale:.3e}; "
+          f"algorithmic flops (22k per term, SURVEY 8d): {flops*scale:.3e}")
+
 if "--check" in sys.argv:
     import oracle
     # reference-style sequential sampler on the oracle's permanent_laplace for the first shots
