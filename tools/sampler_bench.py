@@ -22,6 +22,7 @@ print("first samples:", samples[:2])
 if "--account" in sys.argv:
     # Gray-code terms actually walked: replay the shots' occupations on the host
     import numpy as np
+    gpu_s = sampling.TIMERS.get("  of which GPU kernels (CUDA events)", 0.0)
     terms = 0.0; flops = 0.0
     for smp_i, smp in enumerate(samples[: min(shots, 500)]):
         # the order in which photons were placed is not recorded; the term count of
@@ -42,7 +43,8 @@ if "--account" in sys.argv:
             out[(cdf <= rng.random()).sum()] += 1
         assert tuple(out) == smp
     scale = shots / min(shots, 500)
-    gpu_s = sampling.TIMERS.get("  of which GPU kernels (CUDA events)", 0.0)
+    print(f"GPU kernel time {gpu_s:.3f} s -> {terms*scale/gpu_s/1e9:.2f} G terms/s, "
+          f"{flops*scale/gpu_s/1e12:.2f} algorithmic TFLOP/s")
     print(f"Gray-code terms walked (extrapolated from {min(shots,500)} shots): {terms*scale:.3e}; "
           f"algorithmic flops (22k per term, SURVEY 8d): {flops*scale:.3e}")
 
