@@ -492,3 +492,21 @@ def test_permanent_batch_and_detection_probabilities():
     # golden values of the reference's tests (tests/_simulators/passive/test_preparations.py:231-282)
     with pytest.raises(RuntimeError):
         permanent_batch(u, [[1, 0, 0, 0, 0]], [[1, 1, 0, 0, 0]])
+
+
+def test_haar_submatrices_up_to_n28_against_the_arbiter():
+    """north_star: relative 1e-10 on complex128 Haar-random unitary submatrices.
+    The arbiter is the long-double restatement; the reference's own double
+    arithmetic is measured beside it (it is ~1e-10..1e-9 off at these sizes,
+    SURVEY.md section 0), so agreement with the reference itself can only be
+    asserted at the reference's own error."""
+    big = haar(60, 60)
+    for n in (16, 22, 26, 28):
+        a = np.ascontiguousarray(big[:n, 7:7 + n])
+        ones = np.ones(n, np.int32)
+        truth = oracle.permanent(a, ones, ones, precision=1, njobs=256)
+        got = complex(permanent(a, ones, ones))
+        assert relerr(got, truth) < 1e-10, n
+        if n <= 26:
+            ref_like = oracle.permanent(a, ones, ones, njobs=64)  # the reference's arithmetic
+            assert relerr(got, ref_like) < max(1e-10, 3 * relerr(ref_like, truth)), n
