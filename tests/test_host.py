@@ -187,3 +187,15 @@ def test_numpy_choice_equivalences():
         u = b.random()
         assert x == cdf.searchsorted(u, side="right") == (cdf <= u).sum()
         assert a.random() == b.random()
+
+
+def test_connector_factory_reports_missing_piquasso():
+    """piquasso itself is not a dependency: the plugin connector is built on demand."""
+    import importlib.util
+    from piquasso_b200.connector import make_connector
+    if importlib.util.find_spec("piquasso") is None:
+        with pytest.raises(ImportError, match="piquasso is not importable"):
+            make_connector()
+    else:
+        conn = make_connector()
+        assert hasattr(conn, "permanent") and hasattr(conn, "permanent_laplace")
