@@ -21,7 +21,7 @@ OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libpqperm.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ARCH + (["-DPQ_TUNING"] if os.environ.get("PQ_TUNING") else []) + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
                      "-Xcompiler", "-Wall", "-Xcompiler", "-Wextra"]
 
 # column ranges of the binary constant-bank kernel, one translation unit each

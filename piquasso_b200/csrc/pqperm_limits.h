@@ -2,7 +2,6 @@
 #pragma once
 
 #include <cstdint>
-#include <cstdlib>
 
 namespace pqperm {
 
@@ -31,13 +30,6 @@ struct LapVariant {
 };
 inline LapVariant laplace_variant(int nc)
 {
-#ifdef PQ_TUNING
-    if (const char *e = std::getenv("PQ_LAP_S4_FROM")) {
-        const int from = std::atoi(e);
-        if (nc >= from && nc >= 25)
-            return {4, (nc + 3) / 4};
-    }
-#endif
     if (nc <= 8)
         return {1, nc < 1 ? 1 : nc};
     if (nc <= 26)
