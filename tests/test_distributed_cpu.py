@@ -62,7 +62,7 @@ def test_two_ranks_gloo_sum_to_the_permanent():
                       rng.multinomial(nph, np.ones(d) / d).astype(np.int32),
                       rng.multinomial(nph, np.ones(d) / d).astype(np.int32)))
     world = 2
-    manager = mp.Manager()
+    manager = mp.get_context("spawn").Manager()
     results = manager.dict()
     mp.spawn(_worker, args=(world, _free_port(), cases, results), nprocs=world, join=True)
     assert set(results.keys()) == {0, 1}
@@ -107,7 +107,7 @@ def test_sampler_shots_sharded_over_two_ranks():
     single-process sample list (same per-shot seeds)."""
     from piquasso_b200 import sampling
     world = 2
-    manager = mp.Manager()
+    manager = mp.get_context("spawn").Manager()
     results = manager.dict()
     mp.spawn(_sampler_worker, args=(world, _free_port(), results), nprocs=world, join=True)
     saved = sampling.sampler_pmf
