@@ -205,6 +205,18 @@ def test_full_size_properties_n36():
     assert np.isclose(permanent(np.eye(n, dtype=complex), ones, ones), 1.0)
 
 
+def test_full_size_n40_closed_form():
+    """BASELINE config 5 at full size (2^39 terms, ~8 s on one B200): rank-1
+    unit-modulus matrix against n! prod(u) prod(v)."""
+    n = 40
+    rng = np.random.default_rng(0)
+    u = np.exp(2j * np.pi * rng.random(n))
+    v = np.exp(2j * np.pi * rng.random(n))
+    exact = math.factorial(n) * np.prod(u) * np.prod(v)
+    got = complex(permanent(np.outer(u, v), np.ones(n, np.int32), np.ones(n, np.int32)))
+    assert relerr(got, exact) < 1e-9
+
+
 def test_invariances_haar_n26():
     n = 26
     a = haar(n, 5)
