@@ -199,3 +199,19 @@ def test_connector_factory_reports_missing_piquasso():
     else:
         conn = make_connector()
         assert hasattr(conn, "permanent") and hasattr(conn, "permanent_laplace")
+
+
+def test_plain_c_program_links_against_the_abi(tmp_path):
+    """include/pqperm.h + libpqperm.so from a C translation unit (gcc -std=c99)."""
+    import subprocess
+    from piquasso_b200 import _lib as L
+    exe = tmp_path / "c_abi_smoke"
+    libdir = os.path.dirname(L.LIB_PATH)
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic",
+                    "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", str(exe),
+                    "-L", libdir, "-lpqperm", "-Wl,-rpath," + libdir], check=True)
+    proc = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert proc.returncode == 0, (proc.returncode, proc.stdout, proc.stderr)
+    assert "c abi ok" in proc.stdout
