@@ -522,3 +522,26 @@ def test_haar_submatrices_up_to_n28_against_the_arbiter():
         if n <= 26:
             ref_like = oracle.permanent(a, ones, ones, njobs=64)  # the reference's arithmetic
             assert relerr(got, ref_like) < max(1e-10, 3 * relerr(ref_like, truth)), n
+
+
+def test_concurrent_callers_are_serialised_correctly():
+    """dask worker threads call the connector concurrently (Config.use_dask,
+    sampling.py:174-188 of the reference); the library serialises them."""
+    import threading
+    mats = [haar(10 + (i % 5), 200 + i) for i in range(12)]
+    want = [oracle.permanent(m, np.ones(len(m), int), np.ones(len(m), int), precision=1) for m in mats]
+    got = [None] * len(mats)
+
+    def work(tid):
+        for i in range(tid, len(mats), 4):
+            for _ in range(5):
+                got[i] = complex(permanent(mats[i], np.ones(len(mats[i]), np.int32),
+                                           np.ones(len(mats[i]), np.int32)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for g, w in zip(got, want):
+        assert relerr(g, w) < 1e-10

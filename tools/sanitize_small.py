@@ -1,0 +1,36 @@
+"""Small invocations of every kernel family, for compute-sanitizer (memcheck / racecheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from scipy.stats import unitary_group
+import oracle
+from piquasso_b200 import _lib
+from piquasso_b200._math.permanent import permanent, permanent_laplace
+from piquasso_b200.sampling import permanent_batch, sampler_pmf, grad_perm, permanent_laplace_batch
+
+lib = _lib.load()
+rng = np.random.default_rng(0)
+def chk(a, b, what):
+    assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (what, a, b)
+for n, choice in ((9, 1), (12, 22), (12, 32), (13, 42), (10, 0)):
+    U = unitary_group.rvs(n, random_state=n); ones = np.ones(n, np.int32)
+    lib.pq_set_kernel_choice(choice)
+    chk(complex(permanent(U, ones, ones)), oracle.permanent(U, ones, ones), ("perm", n, choice))
+lib.pq_set_kernel_choice(0)
+U = unitary_group.rvs(6, random_state=6)
+rows = np.array([1, 1, 0, 3, 2, 2]); cols = np.array([2, 1, 3, 0, 1, 2])
+for hint in (0, 1, 7):
+    lib.pq_set_seg_len_hint(hint)
+    chk(complex(permanent(U, rows, cols)), oracle.permanent(U, rows, cols), ("nary", hint))
+lib.pq_set_seg_len_hint(0)
+for k in (3, 7, 10, 14, 27):
+    a = (rng.normal(size=(4, k)) + 1j * rng.normal(size=(4, k))) / 2
+    r = rng.multinomial(k - 1, np.ones(4) / 4); c = np.ones(k, int)
+    got = permanent_laplace(a, r, c); want = oracle.permanent_laplace(a, r, c)
+    assert np.allclose(got, want, rtol=1e-8), ("laplace", k)
+U = unitary_group.rvs(8, random_state=8)
+outs = rng.multinomial(3, np.ones(8) / 8, size=20); ins = rng.multinomial(4, np.ones(8) / 8, size=20)
+sampler_pmf(U, outs, ins)
+permanent_batch(U, rng.multinomial(3, np.ones(8) / 8, size=30), rng.multinomial(3, np.ones(8) / 8, size=30))
+grad_perm(U[:4, :4], [1, 2, 0, 1], [1, 1, 1, 1])
+print("sanitize_small ok, launches:", lib.pq_launch_count())
