@@ -20,7 +20,13 @@ using namespace pqperm;
 
 namespace {
 
-constexpr int kLapSegLen = 64; // terms per segment (<= kLapMaxSegLen)
+// Terms per segment: every segment is seeded by a direct evaluation (O(D*C) FMAs
+// behind shared-memory latency plus the decode of its Gray digits), which costs
+// ~10 % at 64 terms; long segments are used where the problem still yields
+// thousands of them (measured: k=25 walk 0.465 -> 0.388 ms).
+constexpr int kLapSegLen = 64;
+constexpr int kLapSegLenBig = kLapMaxSegLen;          // 256
+constexpr long long kLapBigProblem = 1LL << 18;       // terms
 
 // What the lean planner extracts from one problem's multiplicity vectors
 // (zeros allowed).  Restates src/permanent_laplace.cpp:49-118 of the reference
@@ -111,11 +117,14 @@ void lap_fill(const LapShape &sh, int ncp, LapProblem &q)
 {
     std::memset(&q, 0, sizeof(q));
     q.D = sh.D;
-    int qd = 0;
-    long long W = 1, total = 1;
-    for (int d = 0; d < sh.D; d++) {
+    long long total = 1;
+    for (int d = 0; d < sh.D; d++)
         total *= (sh.mult[d] + 1);
-        if (qd == d && qd < kMaxLowDigits && W * (sh.mult[d] + 1) <= kLapSegLen) {
+    const int seglen = total >= kLapBigProblem ? kLapSegLenBig : kLapSegLen;
+    int qd = 0;
+    long long W = 1;
+    for (int d = 0; d < sh.D; d++) {
+        if (qd == d && qd < kMaxLowDigits && W * (sh.mult[d] + 1) <= seglen) {
             W *= (sh.mult[d] + 1);
             qd++;
         }
