@@ -23,6 +23,8 @@ LIB = os.path.join(HERE, "libpqperm.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
                      "-Xcompiler", "-Wall", "-Xcompiler", "-Wextra"]
+# extra flags for experiments, e.g. PQ_EXTRA_NVCC_FLAGS="-DPQ_SOMETHING=1"
+NVCC_FLAGS += os.environ.get("PQ_EXTRA_NVCC_FLAGS", "").split()
 
 # column ranges of the binary constant-bank kernel, one translation unit each
 BINARY_PARTS = [(0, 8, 20), (1, 21, 30), (2, 31, 40), (3, 41, 48)]
