@@ -11,7 +11,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpqperm.so")
+LIB_PATH = os.environ.get("PQ_LIB_PATH") or os.path.join(_HERE, "libpqperm.so")
 
 PQ_OK = 0
 PQ_ERR_SUM_MISMATCH = 1

@@ -132,4 +132,12 @@ __device__ __forceinline__ void cmul(double &pr, double &pi, double sr, double s
     pi = ni;
 }
 
+// complex multiply-accumulate: (ar, ai) += (pr, pi) * (sr, si); 4 DFMA
+__device__ __forceinline__ void cfma(double &ar, double &ai, double pr, double pi, double sr,
+                                     double si)
+{
+    ar = __fma_rn(pr, sr, __fma_rn(-pi, si, ar));
+    ai = __fma_rn(pr, si, __fma_rn(pi, sr, ai));
+}
+
 } // namespace pqperm

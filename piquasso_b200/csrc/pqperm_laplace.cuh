@@ -36,7 +36,11 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
 {
     constexpr int NCP = NCL * S;
     constexpr int NT = kLapThreads;
-    constexpr int CH = NCL >= 10 ? 3 : (NCL >= 5 ? 2 : 1); // independent chains per lane
+    // independent suffix / prefix chains per lane.  Two are enough once the
+    // next term's row-sum update is interleaved with the prefix pass (measured
+    // on B200: k=25 walk 0.467 ms per 2^23 terms with 3 chunks, 0.453 with 2);
+    // every extra chunk costs 2-3 complex multiplies per term.
+    constexpr int CH = NCL >= 4 ? 2 : 1;
     constexpr int CLEN = (NCL + CH - 1) / CH;              // longest chunk
     extern __shared__ double2 smA[];              // (D+1) x NCP
     __shared__ double s_wtab[kLapMaxSegLen];
@@ -176,28 +180,30 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
         const double factor = valid ? (odd ? -bin : bin) : 0.0;
 
         // ---- walk
+        // The move INTO term m+1 is applied column by column at the end of term
+        // m's prefix pass (right after the last use of s_j): its 2*NCL independent
+        // FMAs and the row loads then fill the latency gaps of the dependent
+        // prefix chains instead of sitting in front of the suffix pass.
+        int p_next = W > 1 ? s_sched[1] : 0;
         for (int m = 0; m < W; ++m) {
-            if (m != 0) {
-                const int p = s_sched[m];
-                const double sg = ((dirmask >> p) & 1u) ? 1.0 : -1.0;
-                dirmask ^= (1u << p) - 1u;
-                const double2 *row = smA + (p + 1) * NCP + h;
-#pragma unroll
-                for (int j = 0; j < NCL; j++) {
-                    const double2 a = row[j * S];
-                    sr[j] = __fma_rn(sg, a.x, sr[j]);
-                    si[j] = __fma_rn(sg, a.y, si[j]);
-                }
-            }
             const double w = factor * s_wtab[m];
+            const bool more = m + 1 < W;
+            const int p = p_next;
+            const double sg = more ? (((dirmask >> p) & 1u) ? 1.0 : -1.0) : 0.0;
+            if (more)
+                dirmask ^= (1u << p) - 1u;
+            p_next = m + 2 < W ? s_sched[m + 2] : 0;
+            // row moved on the next step; after the last term the pinned row (always
+            // present, finite) times sg = 0 leaves s untouched
+            const double2 *row = smA + (more ? p + 1 : 0) * NCP + h;
 
             // ---- all C leave-one-out products of this term -------------------
             // The lane's columns are cut into CH chunks whose suffix / prefix
             // chains are independent (interleaved below so that the FP64 pipe
-            // sees CH chains at once); the product of everything OUTSIDE a chunk
-            // (other chunks, other lanes) is folded into the start value of the
-            // chunk's prefix chain, so no multiply is added per column:
-            //   P_j = start_c * prod_{k<j in chunk} s_k^{c_k} * s_j^{c_j-1} * suf[j+1]
+            // sees CH chains at once); the term weight and the product of
+            // everything OUTSIDE a chunk (other chunks, other lanes) are folded
+            // into the start value of the chunk's prefix chain:
+            //   acc_j += start_c * prod_{k<j in chunk} s_k^{c_k} * s_j^{c_j-1} * suf[j+1]
             double sufr[NCL], sufi[NCL]; // suf[j] = prod_{k >= j, k in chunk(j)} s_k^{c_k}
 #pragma unroll
             for (int i = CLEN - 1; i >= 0; i--) {
@@ -219,11 +225,50 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                     }
                 }
             }
-            // chunk totals -> lane total -> product over the other lanes
-            double lr = sufr[0], li = sufi[0];
+            // lane-local leave-one-chunk-out products out_c = prod_{c' != c} T_c'
+            // (T_c = suf[first column of chunk c]) and the lane total
+            double outr[CH], outi[CH], lr, li;
+            {
+                double pTr[CH], pTi[CH]; // prod_{c' < c} T_c'   (c >= 1)
+                double sTr[CH], sTi[CH]; // prod_{c' > c} T_c'   (c <= CH-2)
 #pragma unroll
-            for (int c = 1; c < CH; c++)
-                cmul(lr, li, sufr[(NCL * c) / CH], sufi[(NCL * c) / CH]);
+                for (int c = 1; c < CH; c++) {
+                    const int f = (NCL * (c - 1)) / CH;
+                    pTr[c] = sufr[f];
+                    pTi[c] = sufi[f];
+                    if (c > 1)
+                        cmul(pTr[c], pTi[c], pTr[c - 1], pTi[c - 1]);
+                }
+#pragma unroll
+                for (int c = CH - 2; c >= 0; c--) {
+                    const int f = (NCL * (c + 1)) / CH;
+                    sTr[c] = sufr[f];
+                    sTi[c] = sufi[f];
+                    if (c < CH - 2)
+                        cmul(sTr[c], sTi[c], sTr[c + 1], sTi[c + 1]);
+                }
+#pragma unroll
+                for (int c = 0; c < CH; c++) {
+                    if (CH == 1) {
+                        outr[c] = 1.0;
+                        outi[c] = 0.0;
+                    } else if (c == 0) {
+                        outr[c] = sTr[0];
+                        outi[c] = sTi[0];
+                    } else if (c == CH - 1) {
+                        outr[c] = pTr[c];
+                        outi[c] = pTi[c];
+                    } else {
+                        outr[c] = pTr[c];
+                        outi[c] = pTi[c];
+                        cmul(outr[c], outi[c], sTr[c], sTi[c]);
+                    }
+                }
+                lr = sufr[0];
+                li = sufi[0];
+                if (CH > 1)
+                    cmul(lr, li, outr[0], outi[0]);
+            }
             double olr = 1.0, oli = 0.0; // other lanes (S > 1 only)
             if (S > 1) {
 #pragma unroll
@@ -244,51 +289,37 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                     cmul(lr, li, olr, oli);
                 fullr = __fma_rn(w, lr, fullr);
                 fulli = __fma_rn(w, li, fulli);
+#pragma unroll
+                for (int j = 0; j < NCL; j++) {
+                    const double2 a = row[j * S];
+                    sr[j] = __fma_rn(sg, a.x, sr[j]);
+                    si[j] = __fma_rn(sg, a.y, si[j]);
+                }
                 continue;
             }
-            // start value of every chunk's prefix chain: everything outside the chunk
+            // start value of every chunk's prefix chain: w * other lanes * out_c.
+            // Carrying w in the chain turns the accumulation into a complex FMA
+            // (acc += pre * suf: 4 DFMA instead of a complex multiply + 2 DFMA).
             double prer[CH], prei[CH];
-            {
-                double lor = olr, loi = oli; // other lanes * chunks before c
-                bool have = S > 1;
+            if (S > 1) {
+                const double wor = w * olr, woi = w * oli;
 #pragma unroll
                 for (int c = 0; c < CH; c++) {
-                    double hr = 1.0, hi2 = 0.0; // chunks after c
-                    bool hhave = false;
-#pragma unroll
-                    for (int c2 = CH - 1; c2 > c; c2--) {
-                        const int f = (NCL * c2) / CH;
-                        if (!hhave) {
-                            hr = sufr[f];
-                            hi2 = sufi[f];
-                            hhave = true;
-                        } else {
-                            cmul(hr, hi2, sufr[f], sufi[f]);
-                        }
-                    }
-                    if (have && hhave) {
-                        prer[c] = lor;
-                        prei[c] = loi;
-                        cmul(prer[c], prei[c], hr, hi2);
-                    } else if (have) {
-                        prer[c] = lor;
-                        prei[c] = loi;
-                    } else {
-                        prer[c] = hr; // (1, 0) when there is nothing outside
-                        prei[c] = hi2;
-                    }
-                    const int f = (NCL * c) / CH;
-                    if (!have) {
-                        lor = sufr[f];
-                        loi = sufi[f];
-                        have = true;
-                    } else {
-                        cmul(lor, loi, sufr[f], sufi[f]);
-                    }
+                    prer[c] = wor;
+                    prei[c] = woi;
+                    if (CH > 1)
+                        cmul(prer[c], prei[c], outr[c], outi[c]);
                 }
-                // lor now holds the product of ALL columns: what a c_l = 0 column gets
-                fullr = __fma_rn(w, lor, fullr);
-                fulli = __fma_rn(w, loi, fulli);
+                // w * the product of ALL columns: what a c_l = 0 column gets
+                cfma(fullr, fulli, wor, woi, lr, li);
+            } else {
+#pragma unroll
+                for (int c = 0; c < CH; c++) {
+                    prer[c] = w * outr[c];
+                    prei[c] = w * outi[c];
+                }
+                fullr = __fma_rn(w, lr, fullr);
+                fulli = __fma_rn(w, li, fulli);
             }
             // prefix chains, interleaved over the chunks
 #pragma unroll
@@ -299,22 +330,24 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                     const int j = j0 + i;
                     if (j < j1) {
                         double pr = prer[c], pi = prei[c];
-                        int cm = 1;
                         if (!UNITCOLS) {
-                            cm = Q.colmult[j * S + h];
+                            const int cm = Q.colmult[j * S + h];
                             for (int k = 1; k < cm; k++)
                                 cmul(pr, pi, sr[j], si[j]); // pre * s_j^{c_j - 1}
                         }
                         if (j + 1 < j1) {
-                            // next start of the chain: pre * s_j^{c_j}
-                            double nr = pr, ni = pi;
-                            cmul(nr, ni, sr[j], si[j]);
-                            prer[c] = nr;
-                            prei[c] = ni;
-                            cmul(pr, pi, sufr[j + 1], sufi[j + 1]);
+                            cfma(accr[j], acci[j], pr, pi, sufr[j + 1], sufi[j + 1]);
+                            cmul(pr, pi, sr[j], si[j]); // next start: pre * s_j^{c_j}
+                            prer[c] = pr;
+                            prei[c] = pi;
+                        } else {
+                            accr[j] += pr;
+                            acci[j] += pi;
                         }
-                        accr[j] = __fma_rn(w, pr, accr[j]);
-                        acci[j] = __fma_rn(w, pi, acci[j]);
+                        // s_j is not needed by this term any more: move to the next term
+                        const double2 a = row[j * S];
+                        sr[j] = __fma_rn(sg, a.x, sr[j]);
+                        si[j] = __fma_rn(sg, a.y, si[j]);
                     }
                 }
             }
