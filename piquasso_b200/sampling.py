@@ -18,7 +18,7 @@ import numpy as np
 from . import _lib
 
 __all__ = ["permanent_laplace_batch", "permanent_batch", "detection_probabilities",
-           "grad_perm", "sampler_pmf", "generate_samples"]
+           "grad_perm", "sampler_pmf", "generate_samples", "generate_lossy_samples"]
 
 # wall-clock split of generate_samples (seconds), for tools/sampler_bench.py
 TIMERS = {}
@@ -197,8 +197,65 @@ def sampler_pmf(interferometer, out_occ, in_occ):
     return pmf
 
 
+def _generate_samples_by_coroutines(input, shots, interferometer, seed_sequence,
+                                    reject_condition, postselect_data,
+                                    uniform_particle_overlap, pmf_rows):
+    """The sampler variants (post-selection, uniform particle overlap) through
+    the lock-step shot engine of :mod:`piquasso_b200.shot_engine`."""
+    from . import shot_engine
+
+    input = np.asarray(input, dtype=int)
+    U = np.ascontiguousarray(interferometer, dtype=np.complex128)
+    d = len(input)
+    n = int(np.sum(input))
+    first_quantized = _to_first_quantized(input)
+    postselected = postselect_data is not None and len(postselect_data[0]) > 0
+
+    def coroutine(idx, reject):
+        rng = np.random.default_rng(seed=seed_sequence + idx)
+        return shot_engine.shot_coroutine(d, n, first_quantized, rng, reject, U,
+                                          postselect_data, uniform_particle_overlap)
+
+    if reject_condition is not None and postselected:
+        # The number of reject_condition() calls of a post-selected shot depends
+        # on its retries, and the reference's condition draws from one generator
+        # shared by all shots (simulation_steps.py:350-360): only the reference's
+        # own shot-after-shot order reproduces it.
+        results = []
+        for idx in range(shots):
+            results.extend(shot_engine.run_shots([coroutine(idx, reject_condition)], U,
+                                                 pmf_rows))
+    else:
+        if reject_condition is None:
+            rejects = [lambda: False] * shots
+        else:
+            # exactly n calls per shot, shot after shot: evaluate them up front
+            drawn = [[bool(reject_condition()) for _ in range(n)] for _ in range(shots)]
+            rejects = [iter(row).__next__ for row in drawn]
+        results = shot_engine.run_shots([coroutine(idx, rejects[idx])
+                                         for idx in range(shots)], U, pmf_rows)
+    return [tuple(int(x) for x in sample) for sample in results]
+
+
+def generate_lossy_samples(input, shots, interferometer, seed_sequence, postselect_data=None,
+                           pmf_rows=None):
+    """Non-uniform losses (``generate_lossy_samples``, sampling.py:110-146 of the
+    reference): sample the 2d-mode unitary dilation of the lossy transfer matrix
+    and keep the first d modes."""
+    from . import shot_engine
+
+    input = np.asarray(input, dtype=int)
+    expanded = shot_engine.expanded_interferometer(np.asarray(interferometer))
+    expanded_input = np.concatenate([input, np.zeros_like(input)])
+    samples = generate_samples(expanded_input, shots, expanded, seed_sequence,
+                               reject_condition=None, postselect_data=postselect_data,
+                               pmf_rows=pmf_rows)
+    return [s[: len(input)] for s in samples]
+
+
 def generate_samples(input, shots, interferometer, seed_sequence, reject_condition=None,
-                     batch_shots=None):
+                     batch_shots=None, postselect_data=None, uniform_particle_overlap=None,
+                     pmf_rows=None):
     """Clifford & Clifford algorithm B, all shots in lock step.
 
     Restates ``_generate_samples`` / ``_generate_sample`` / ``_calculate_pmf``
@@ -221,9 +278,23 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
     state-independent callable the reference evaluates once per photon per shot
     in shot-major order, possibly drawing from a shared generator; it is
     therefore evaluated up front in that same order.
+
+    ``postselect_data = (modes, photons, max_trials)`` and
+    ``uniform_particle_overlap`` select the reference's other per-shot
+    algorithms (sampling.py:73-97); those run through the coroutine engine of
+    :mod:`piquasso_b200.shot_engine`, still one batched GPU call per round.
+    ``pmf_rows`` replaces :func:`sampler_pmf` (tests inject the oracle there to
+    exercise the host logic without a GPU).
     """
     import time
 
+    if pmf_rows is None:
+        pmf_rows = sampler_pmf
+    if ((postselect_data is not None and len(postselect_data[0]) > 0)
+            or uniform_particle_overlap is not None):
+        return _generate_samples_by_coroutines(input, shots, interferometer, seed_sequence,
+                                               reject_condition, postselect_data,
+                                               uniform_particle_overlap, pmf_rows)
     input = np.asarray(input, dtype=int)
     U = np.ascontiguousarray(interferometer, dtype=np.complex128)
     d = len(input)
@@ -265,7 +336,7 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
             remaining[live] -= 1
             _tick("host: grow input", t0)
             t0 = time.perf_counter()
-            pmf = sampler_pmf(U, sample[live], current_input[live])
+            pmf = pmf_rows(U, sample[live], current_input[live])
             _tick("pq_sampler_pmf_c128 (filter + plan + GPU walk + pmf)", t0)
             t0 = time.perf_counter()
             # _calculate_pmf normalisation (sequential sum) and _sample_from_pmf:

@@ -56,6 +56,46 @@ def relerr(a, b):
     return abs(a - b) / max(abs(b), 1e-300)
 
 
+def oracle_pmf_rows(interferometer, out_occ, in_occ):
+    """Unnormalised pmf rows of the sampler's photon step computed with the
+    ORACLE's permanent_laplace (the reference's _calculate_pmf,
+    piquasso/_simulators/passive/sampling.py:723-749): the CPU stand-in for
+    piquasso_b200.sampling.sampler_pmf when only the host logic is under test."""
+    import oracle
+    u = np.asarray(interferometer, dtype=np.complex128)
+    rows = []
+    for out, inp in zip(np.atleast_2d(out_occ), np.atleast_2d(in_occ)):
+        inz, onz = inp > 0, out > 0
+        part = oracle.permanent_laplace(u[np.ix_(onz, inz)], out[onz], inp[inz])
+        amp = np.zeros(u.shape[0], dtype=np.complex128)
+        for j, col in enumerate(np.flatnonzero(inz)[: len(part)]):
+            amp += inp[col] * part[j] * u[:, col]
+        rows.append(np.abs(amp) ** 2)
+    return np.array(rows)
+
+
+def run_sampler_variant(case, pmf_rows=None):
+    """Replay one case of tests/golden/sampler_variants.json through
+    piquasso_b200.sampling (pmf_rows=None: the CUDA path)."""
+    from piquasso_b200 import sampling
+    u = golden_matrix(case["interferometer"])
+    postselect = (tuple(case["postselect_modes"]), tuple(case["postselect_photons"]),
+                  case["max_trials"])
+    if case["lossy_dilation"]:
+        return sampling.generate_lossy_samples(case["input"], case["shots"], u,
+                                               case["seed_sequence"],
+                                               postselect_data=postselect, pmf_rows=pmf_rows)
+    reject = None
+    if case["loss"]:
+        shared = np.random.default_rng(case["loss"][0])
+        transmission = case["loss"][1]
+        reject = lambda: shared.uniform() > transmission  # noqa: E731
+    return sampling.generate_samples(case["input"], case["shots"], u, case["seed_sequence"],
+                                     reject_condition=reject, postselect_data=postselect,
+                                     uniform_particle_overlap=case["overlap"],
+                                     pmf_rows=pmf_rows)
+
+
 def _ensure_built():
     """The .so files are git-ignored build products; a checkout that has not run
     __graft_entry__.build() yet gets them built once (nvcc / gcc, no GPU needed)."""

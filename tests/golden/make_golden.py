@@ -222,6 +222,62 @@ def main():
     ref_steps.generate_samples = orig_generate
     print("sampler goldens:", len(sampler_cases), "laplace calls kept:", len(laplace_cases))
 
+
+    # ---- 3b. the other per-shot algorithms of the sampler ----------
+    # post-selection, uniform particle overlap, both, non-uniform losses: the
+    # reference's generate_samples / generate_lossy_samples called directly with
+    # seeded per-shot generators; reject conditions that draw from a shared
+    # generator are described by (seed, transmission) so that a test can rebuild
+    # them.
+    from types import SimpleNamespace
+    from scipy.stats import unitary_group as _ug
+    variant_cases = []
+
+    def run_variant(label, input, shots, U, seed, postselect=((), (), 1000), overlap=None,
+                    loss=None, lossy_dilation=False):
+        config = SimpleNamespace(seed_sequence=seed, use_dask=False)
+        if loss is None:
+            reject = lambda: False  # noqa: E731
+        else:
+            shared = np.random.default_rng(loss[0])
+            reject = lambda: shared.uniform() > loss[1]  # noqa: E731
+        if lossy_dilation:
+            samples = ref_sampling.generate_lossy_samples(
+                np.array(input), shots, oracle.ref_permanent_laplace, U, postselect, config)
+        else:
+            samples = orig_generate(np.array(input), shots, oracle.ref_permanent_laplace, U,
+                                    reject, postselect, overlap, config)
+        variant_cases.append({
+            "label": label, "input": [int(x) for x in input], "shots": shots,
+            "interferometer": _mat(U), "seed_sequence": seed,
+            "postselect_modes": [int(x) for x in postselect[0]],
+            "postselect_photons": [int(x) for x in postselect[1]],
+            "max_trials": int(postselect[2]), "overlap": overlap,
+            "loss": list(loss) if loss else None, "lossy_dilation": lossy_dilation,
+            "samples": [[int(x) for x in smp] for smp in samples]})
+
+    U6 = _ug.rvs(6, random_state=606)
+    U5 = _ug.rvs(5, random_state=505)
+    lossy5 = U5 @ np.diag(np.sqrt([0.9, 0.5, 0.7, 0.95, 0.3])) @ _ug.rvs(5, random_state=506)
+    run_variant("postselect one mode", [1, 1, 1, 1, 0, 0], 40, U6, 11,
+                postselect=((2,), (1,), 1000))
+    run_variant("postselect two modes, bunched input", [2, 0, 1, 1, 0, 0], 40, U6, 12,
+                postselect=((0, 4), (1, 0), 1000))
+    run_variant("uniform overlap", [1, 1, 2, 0, 1, 0], 40, U6, 13, overlap=0.6)
+    run_variant("uniform overlap + uniform loss", [1, 1, 2, 0, 1, 0], 40, 0.8 ** 0.5 * U6, 14,
+                overlap=0.35, loss=(99, 0.8))
+    # (with an exactly unitary matrix the reference's loss weight 1 - sum|u|^2 comes
+    # out as -1e-16 and numpy rejects the weights: the combination needs losses)
+    run_variant("postselect + uniform overlap + uniform loss", [1, 1, 1, 1, 0, 0], 30,
+                0.9 ** 0.5 * U6, 15, postselect=((1,), (1,), 1000), overlap=0.5, loss=(5, 0.9))
+    run_variant("postselect + uniform loss (sequential reject order)", [1, 1, 1, 1, 0, 0], 30,
+                0.9 ** 0.5 * U6, 16, postselect=((3,), (1,), 1000), loss=(7, 0.9))
+    run_variant("non-uniform losses (2d dilation)", [1, 1, 1, 0, 0], 40, lossy5, 17,
+                lossy_dilation=True)
+    run_variant("non-uniform losses + postselect", [1, 1, 1, 0, 0], 30, lossy5, 18,
+                postselect=((0,), (1,), 1000), lossy_dilation=True)
+    print("sampler variant goldens:", len(variant_cases))
+
     # ---- 4. seeded Haar cases against the compiled reference ---------------------
     from scipy.stats import unitary_group
     rng = np.random.default_rng(2024)
@@ -288,6 +344,7 @@ def main():
         "permanent_haar.json": haar_cases,
         "laplace.json": laplace_cases,
         "sampler.json": sampler_cases,
+        "sampler_variants.json": variant_cases,
         "gray.json": gray_cases,
     }
     for fname, payload in out.items():

@@ -545,3 +545,13 @@ def test_concurrent_callers_are_serialised_correctly():
         t.join()
     for g, w in zip(got, want):
         assert relerr(g, w) < 1e-10
+
+
+def test_sampler_variant_goldens_identical_samples():
+    """Post-selected, partially distinguishable and lossy samplers
+    through the shot engine with the CUDA pmf call: identical samples to the
+    reference run with the same seeds (tests/golden/sampler_variants.json)."""
+    from conftest import run_sampler_variant
+    for case in load_golden("sampler_variants.json"):
+        got = run_sampler_variant(case)
+        assert [list(s) for s in got] == case["samples"], case["label"]

@@ -215,3 +215,59 @@ def test_plain_c_program_links_against_the_abi(tmp_path):
     proc = subprocess.run([str(exe)], capture_output=True, text=True)
     assert proc.returncode == 0, (proc.returncode, proc.stdout, proc.stderr)
     assert "c abi ok" in proc.stdout
+
+
+# ---- sampler host logic with the oracle standing in for the GPU call ---------
+
+def test_lockstep_sampler_host_logic_against_reference_goldens():
+    """generate_samples' vectorised host bookkeeping (per-shot RNG order, input
+    growth, normalisation, draw) on the reference's seeded goldens
+    (tests/_simulators/passive/test_measurements.py:237-561), the pmf rows coming
+    from the oracle instead of pq_sampler_pmf_c128."""
+    from conftest import golden_matrix, load_golden, oracle_pmf_rows
+    from piquasso_b200.sampling import generate_samples
+    for case in load_golden("sampler.json"):
+        if len(case["input"]) > 8 or case["shots"] > 200:
+            continue  # keep the CPU suite short; the GPU suite replays all of them
+        it = iter(list(case["rejects"]))
+        got = generate_samples(case["input"], case["shots"],
+                               golden_matrix(case["interferometer"]), case["seed_sequence"],
+                               reject_condition=lambda: next(it), pmf_rows=oracle_pmf_rows)
+        assert [list(s) for s in got] == case["samples"], case["source"]
+
+
+def test_sampler_variants_host_logic_against_reference_goldens():
+    """Post-selected / partially distinguishable / lossy per-shot algorithms
+    (piquasso/_simulators/passive/sampling.py:110-146, 239-529) as shot coroutines:
+    identical samples to the reference run with the same seeds
+    (tests/golden/sampler_variants.json, made by make_golden.py section 3b)."""
+    from conftest import load_golden, oracle_pmf_rows, run_sampler_variant
+    cases = load_golden("sampler_variants.json")
+    assert len(cases) >= 8
+    for case in cases:
+        got = run_sampler_variant(case, pmf_rows=oracle_pmf_rows)
+        assert [list(s) for s in got] == case["samples"], case["label"]
+
+
+def test_postselection_gives_up_after_max_trials():
+    from conftest import haar, oracle_pmf_rows
+    from piquasso_b200.sampling import generate_samples
+    from piquasso_b200.shot_engine import InvalidSimulation
+    u = haar(4, 4)
+    with pytest.raises(InvalidSimulation):
+        # three photons can never leave four in mode 0
+        generate_samples([1, 1, 1, 0], 2, u, 3, postselect_data=((0,), (4,), 5),
+                         pmf_rows=oracle_pmf_rows)
+
+
+def test_expanded_interferometer_embeds_the_lossy_matrix_isometrically():
+    from conftest import haar
+    from piquasso_b200.shot_engine import expanded_interferometer
+    lossy = haar(5, 1) @ np.diag(np.sqrt([0.9, 0.2, 0.5, 0.7, 0.6])) @ haar(5, 2)
+    big = expanded_interferometer(lossy)
+    assert big.shape == (10, 10)
+    assert np.allclose(big[:5, :5], lossy)
+    # the photons enter in the first d modes only: those columns must be orthonormal
+    # (the reference's [[S, C], [C, S]] middle factor is not unitary as a whole)
+    left = big[:, :5]
+    assert np.allclose(left.conj().T @ left, np.eye(5), atol=1e-12)
