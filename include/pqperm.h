@@ -118,6 +118,20 @@ int pq_sampler_pmf_c128(const double *U, int d, int nshots, const int32_t *out_o
                         const int32_t *in_occ, double *pmf);
 
 /* ---------------------------------------------------------------------
+ * The same photon step including the draw (_calculate_pmf's normalisation and
+ * _sample_from_pmf, piquasso/_simulators/passive/sampling.py:736-753): the pmf
+ * rows stay on the device and index[s] is the output mode that
+ * rng.choice(arange(d), p=pmf) returns when the shot's generator yields the
+ * uniform variate u[s] -- numpy's Generator.choice(a, p=p) is
+ * searchsorted(cumsum(p) / cumsum(p)[-1], rng.random(), side="right"), so the
+ * caller draws u[s] = rng.random() from shot s's own generator (which does not
+ * depend on the pmf) and this call repeats numpy's arithmetic in numpy's
+ * order.  index[s] = -1 marks a row numpy would reject (NaN probabilities).
+ * ------------------------------------------------------------------- */
+int pq_sampler_draw_c128(const double *U, int d, int nshots, const int32_t *out_occ,
+                         const int32_t *in_occ, const double *u, int32_t *index);
+
+/* ---------------------------------------------------------------------
  * Partitioned permanent: the piece of one permanent that rank `part` of
  * `nparts` owns.  The term space [0, idx_max) (src/permanent.cpp:131-142) is
  * cut into equal-length Gray-code segments (one per GPU thread; the

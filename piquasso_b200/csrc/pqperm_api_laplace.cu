@@ -169,12 +169,16 @@ struct Buckets {
         }
     }
 };
-Buckets g_buckets; // guarded by g_mu; keeps its capacity between calls
+// per calling thread (the sampler step plans outside the library lock); keeps its
+// capacity between calls
+thread_local Buckets g_buckets;
 
 struct Epilogue {
     const double2 *d_U = nullptr; // gather mode / sampler: matrix on the device
     int ldu = 0;
     double *pmf = nullptr;        // sampler: host [nshots][ldu], row = LapProblem.tag
+    const double *u = nullptr;    // sampler draw: host [nshots] uniform variates ...
+    int32_t *index = nullptr;     // ... and the drawn output modes (the pmf stays on the device)
     bool perm_only = false;       // batched permanents: only the full product
 };
 
@@ -233,7 +237,30 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
     void *h_dst = nullptr;
     size_t bytes = 0;
     const void *d_src = nullptr;
-    if (epi && epi->pmf) {
+    if (epi && epi->index) {
+        bytes = (size_t)n * sizeof(int32_t);
+        if ((rc = grow_dev(c, 5, (size_t)n * epi->ldu * sizeof(double))) ||
+            (rc = grow_dev(c, 6, (size_t)n * sizeof(double))) || (rc = grow_dev(c, 7, bytes)) ||
+            (rc = grow_host(c, 0, (size_t)n * sizeof(double))) || (rc = grow_host(c, 1, bytes)))
+            return rc;
+        double *hu = reinterpret_cast<double *>(c->h_lap[0]);
+        for (int i = 0; i < n; i++)
+            hu[i] = epi->u[bk.probs[i].tag];
+        PQ_CUDA(cudaMemcpyAsync(c->d_lap[6], hu, (size_t)n * sizeof(double),
+                                cudaMemcpyHostToDevice, st));
+        e = launch_sampler_pmf(P, ncp1, epi->d_U, epi->ldu,
+                               reinterpret_cast<double *>(c->d_lap[5]), st);
+        if (e != cudaSuccess)
+            return fail_cuda(e, "launch sampler_pmf_kernel");
+        e = launch_sampler_draw(reinterpret_cast<const double *>(c->d_lap[5]), n, epi->ldu,
+                                reinterpret_cast<const double *>(c->d_lap[6]),
+                                reinterpret_cast<int *>(c->d_lap[7]), st);
+        if (e != cudaSuccess)
+            return fail_cuda(e, "launch sampler_draw_kernel");
+        g_launches += 2;
+        h_dst = c->h_lap[1];
+        d_src = c->d_lap[7];
+    } else if (epi && epi->pmf) {
         bytes = (size_t)n * epi->ldu * sizeof(double);
         if ((rc = grow_dev(c, 5, bytes)) || (rc = grow_host(c, 3, bytes)))
             return rc;
@@ -257,7 +284,11 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
         c->last_kernel_ms = (c->last_kernel_ms < 0 ? 0.0 : c->last_kernel_ms) + ms;
-    if (epi && epi->pmf) {
+    if (epi && epi->index) {
+        const int32_t *src = reinterpret_cast<const int32_t *>(c->h_lap[1]);
+        for (int i = 0; i < n; i++)
+            epi->index[bk.probs[i].tag] = src[i];
+    } else if (epi && epi->pmf) {
         const double *src = reinterpret_cast<const double *>(c->h_lap[3]);
         for (int i = 0; i < n; i++)
             std::memcpy(epi->pmf + (size_t)bk.probs[i].tag * epi->ldu, src + (size_t)i * epi->ldu,
@@ -354,13 +385,49 @@ int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const
 }
 
 // One photon step of the sampler for nshots shots sharing one interferometer.
-int sampler_pmf_locked(const double *U, int d, int nshots, const int32_t *out_occ,
-                       const int32_t *in_occ, double *pmf)
+// numpy's Generator.choice(d, p = row / sum(row)) for the uniform variate u, on
+// the host (shots whose Laplace problem is the reference's early-out)
+int draw_from_row(const double *row, int d, double u)
 {
-    DeviceCtx *c = nullptr;
-    int rc = ctx_get(g_devices[0], &c);
-    if (rc)
-        return rc;
+    double total = 0.0;
+    for (int m = 0; m < d; m++)
+        total += row[m];
+    double last = 0.0;
+    for (int m = 0; m < d; m++)
+        last += row[m] / total;
+    double c = 0.0;
+    int idx = 0;
+    for (int m = 0; m < d; m++) {
+        c += row[m] / total;
+        idx += (c / last <= u) ? 1 : 0;
+    }
+    return last == last ? idx : -1;
+}
+
+// pmf != nullptr: return the unnormalised pmf rows.  Otherwise draw on the
+// device: index[s] = the output mode numpy's choice would pick for u[s].
+int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
+                 const int32_t *in_occ, double *pmf, const double *u = nullptr,
+                 int32_t *index = nullptr)
+{
+    // Planning (zero filtering, shapes, problem descriptors) touches only the
+    // caller's arguments and this thread's buckets: it runs OUTSIDE the library
+    // lock, so that one thread can plan its photon step while another thread's
+    // step occupies the GPU.
+    {
+        // ... but never without a device: there is no CPU path, not even for the
+        // shots that need no kernel
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            std::lock_guard<std::mutex> lock(g_mu);
+            DeviceCtx *c0 = nullptr;
+            const int rc0 = ctx_get(g_devices[0], &c0);
+            return rc0 ? rc0 : fail(PQ_ERR_NO_DEVICE, "no usable CUDA device");
+        }
+    }
+    std::vector<double> trivial_row(pmf ? 0 : d);
+    int rc = PQ_OK;
     std::string err;
     LapShape sh;
     g_buckets.reset();
@@ -373,7 +440,7 @@ int sampler_pmf_locked(const double *U, int d, int nshots, const int32_t *out_oc
         rc = lap_shape(d, d, oo, io, sh, err);
         if (rc)
             return fail(rc, err);
-        double *prow = pmf + (size_t)s * d;
+        double *prow = pmf ? pmf + (size_t)s * d : trivial_row.data();
         if (sh.trivial) {
             // permanent_laplace returns [1] (src/permanent_laplace.cpp:52-57) and
             // _calculate_pmf then uses the first non-zero input mode only
@@ -391,6 +458,8 @@ int sampler_pmf_locked(const double *U, int d, int nshots, const int32_t *out_oc
                 }
                 prow[m] = v;
             }
+            if (!pmf)
+                index[s] = draw_from_row(prow, d, u[s]);
             continue;
         }
         const LapVariant v = laplace_variant(sh.NC);
@@ -409,6 +478,10 @@ int sampler_pmf_locked(const double *U, int d, int nshots, const int32_t *out_oc
     }
     if (!any)
         return PQ_OK;
+    std::lock_guard<std::mutex> lock(g_mu);
+    DeviceCtx *c = nullptr;
+    if ((rc = ctx_get(g_devices[0], &c)))
+        return rc;
     const size_t ubytes = (size_t)d * d * sizeof(double2);
     if ((rc = grow_dev(c, 4, ubytes)))
         return rc;
@@ -417,6 +490,8 @@ int sampler_pmf_locked(const double *U, int d, int nshots, const int32_t *out_oc
     epi.d_U = reinterpret_cast<const double2 *>(c->d_lap[4]);
     epi.ldu = d;
     epi.pmf = pmf;
+    epi.u = u;
+    epi.index = pmf ? nullptr : index;
     c->last_kernel_ms = -1.0;
     for (Bucket &bk : g_buckets.b) {
         if (bk.probs.empty())
@@ -527,8 +602,18 @@ extern "C" int pq_sampler_pmf_c128(const double *U, int d, int nshots, const int
         return fail(PQ_ERR_BAD_ARG, "bad sampler arguments");
     if (nshots == 0)
         return PQ_OK;
-    std::lock_guard<std::mutex> lock(g_mu);
-    return sampler_pmf_locked(U, d, nshots, out_occ, in_occ, pmf);
+    return sampler_step(U, d, nshots, out_occ, in_occ, pmf);
+}
+
+extern "C" int pq_sampler_draw_c128(const double *U, int d, int nshots, const int32_t *out_occ,
+                                    const int32_t *in_occ, const double *u, int32_t *index)
+{
+    if (d < 1 || d > 65535 || nshots < 0 || !U ||
+        (nshots > 0 && (!out_occ || !in_occ || !u || !index)))
+        return fail(PQ_ERR_BAD_ARG, "bad sampler arguments");
+    if (nshots == 0)
+        return PQ_OK;
+    return sampler_step(U, d, nshots, out_occ, in_occ, nullptr, u, index);
 }
 
 extern "C" int pq_perm_laplace_batch_c128(int nprob, const double *A, const int64_t *a_off,

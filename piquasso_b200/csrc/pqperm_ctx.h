@@ -41,9 +41,11 @@ struct DeviceCtx {
     cudaEvent_t ring0[kTimingRing], ring1[kTimingRing];  // event pairs around the kernels
     uint64_t ring_next = 0;
     // growable scratch of the batched Laplace path
-    void *d_lap[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // prob, A2, partials, out, U, pmf
-    size_t d_lap_cap[6] = {0, 0, 0, 0, 0, 0};
-    void *h_lap[4] = {nullptr, nullptr, nullptr, nullptr}; // unused, unused, out, pmf (pinned)
+    // prob, A2, partials, out, U, pmf, uniform draws, drawn indices
+    void *d_lap[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t d_lap_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // (pinned) uniform draws, drawn indices, out, pmf
+    void *h_lap[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t h_lap_cap[4] = {0, 0, 0, 0};
 };
 

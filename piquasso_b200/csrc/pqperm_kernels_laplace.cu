@@ -78,6 +78,13 @@ cudaError_t launch_sampler_pmf(const LapParams &P, int ncp1, const double2 *U, i
     sampler_pmf_kernel<<<P.nprob, 128, 0, stream>>>(P, ncp1, U, d, pmf);
     return cudaGetLastError();
 }
+
+cudaError_t launch_sampler_draw(const double *pmf, int n, int d, const double *u, int *index,
+                                cudaStream_t stream)
+{
+    sampler_draw_kernel<<<(n + 127) / 128, 128, 0, stream>>>(pmf, n, d, u, index);
+    return cudaGetLastError();
+}
 #endif
 
 } // namespace pqperm

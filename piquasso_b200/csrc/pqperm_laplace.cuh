@@ -440,4 +440,35 @@ static __global__ void __launch_bounds__(128) sampler_pmf_kernel(const LapParams
     }
 }
 
+// Draw from the pmf rows on the device: what the host does after
+// _calculate_pmf (piquasso/_simulators/passive/sampling.py:736-753 of the
+// reference), i.e. p = pmf / sum(pmf) (sequential sum) and numpy's
+// Generator.choice(a, p=p) = searchsorted(cumsum(p) / cumsum(p)[-1], u, "right"),
+// with the uniform variate u drawn by the caller from the shot's own generator.
+// One thread per shot repeats numpy's operations in numpy's order (sequential
+// adds, IEEE divisions; nothing here can be contracted into an FMA), so the
+// index is the one the host would have computed from the same row.
+static __global__ void __launch_bounds__(128) sampler_draw_kernel(const double *pmf, int n, int d,
+                                                                  const double *u, int *index)
+{
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n)
+        return;
+    const double *row = pmf + (size_t)i * d;
+    double total = 0.0;
+    for (int m = 0; m < d; m++)
+        total += row[m];
+    double last = 0.0;
+    for (int m = 0; m < d; m++)
+        last += row[m] / total;
+    const double ui = u[i];
+    double c = 0.0;
+    int idx = 0;
+    for (int m = 0; m < d; m++) {
+        c += row[m] / total;
+        idx += (c / last <= ui) ? 1 : 0;
+    }
+    index[i] = (last == last) ? idx : -1; // NaN row (all-zero pmf): numpy raises
+}
+
 } // namespace pqperm

@@ -46,5 +46,8 @@ cudaError_t launch_laplace_reduce(const LapParams &P, int ncp1, cudaStream_t str
 // pmf rows of the Clifford-Clifford sampler from the Laplace results of P (device)
 cudaError_t launch_sampler_pmf(const LapParams &P, int ncp1, const double2 *U, int d,
                                double *pmf, cudaStream_t stream);
+// index[i] = numpy's Generator.choice(d, p = pmf row i normalised) for the variate u[i]
+cudaError_t launch_sampler_draw(const double *pmf, int n, int d, const double *u, int *index,
+                                cudaStream_t stream);
 
 } // namespace pqperm

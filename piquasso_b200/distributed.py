@@ -98,7 +98,7 @@ def permanent_allgather(matrix, rows, cols, group=None, device_index=None):
 
 
 def generate_samples_sharded(input, shots, interferometer, seed_sequence,
-                             reject_condition=None, group=None):
+                             reject_condition=None, group=None, pmf_rows=None):
     """The lock-step sampler with the SHOTS sharded over the ranks of ``group``.
 
     Shots are independent (shot ``idx`` owns ``default_rng(seed_sequence + idx)``),
@@ -109,7 +109,8 @@ def generate_samples_sharded(input, shots, interferometer, seed_sequence,
 
     ``reject_condition`` is evaluated by every rank for ALL shots in the
     reference's shot-major order (it may draw from a generator the ranks seeded
-    identically), and each rank keeps its own rows."""
+    identically), and each rank keeps its own rows.  ``pmf_rows`` is handed to
+    :func:`piquasso_b200.sampling.generate_samples` (CPU tests inject the oracle)."""
     import torch.distributed as dist
 
     from .sampling import generate_samples
@@ -126,7 +127,7 @@ def generate_samples_sharded(input, shots, interferometer, seed_sequence,
         flat = iter([x for row in table[begin:end] for x in row])
         rejects = lambda: next(flat)  # noqa: E731
     mine = generate_samples(input, end - begin, interferometer, seed_sequence + begin,
-                            reject_condition=rejects)
+                            reject_condition=rejects, pmf_rows=pmf_rows)
     if world == 1:
         return mine
     gathered = [None] * world

@@ -16,9 +16,11 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib
+from .shot_rng import ShotStreams
 
 __all__ = ["permanent_laplace_batch", "permanent_batch", "detection_probabilities",
-           "grad_perm", "sampler_pmf", "generate_samples", "generate_lossy_samples"]
+           "grad_perm", "sampler_pmf", "sampler_draw", "generate_samples",
+           "generate_lossy_samples"]
 
 # wall-clock split of generate_samples (seconds), for tools/sampler_bench.py
 TIMERS = {}
@@ -197,6 +199,39 @@ def sampler_pmf(interferometer, out_occ, in_occ):
     return pmf
 
 
+def sampler_draw(interferometer, out_occ, in_occ, uniforms):
+    """One photon step including the draw (``pq_sampler_draw_c128``): entry s is
+    ``rng.choice(arange(d), p=_calculate_pmf(in_occ[s], out_occ[s], ...))`` of the
+    reference (sampling.py:723-753) for the generator state in which
+    ``rng.random()`` returns ``uniforms[s]``.  The pmf rows never leave the device:
+    normalisation and numpy's cdf search are repeated there operation by
+    operation."""
+    lib = _lib.load()
+    U = np.ascontiguousarray(interferometer, dtype=np.complex128)
+    d = U.shape[0]
+    if U.shape != (d, d):
+        raise ValueError("interferometer must be square")
+    oo = np.ascontiguousarray(out_occ, dtype=np.int32).reshape(-1, d)
+    io = np.ascontiguousarray(in_occ, dtype=np.int32).reshape(-1, d)
+    u = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(-1)
+    if oo.shape != io.shape or u.shape[0] != oo.shape[0]:
+        raise ValueError("out_occ, in_occ and uniforms describe different numbers of shots")
+    index = np.empty(oo.shape[0], dtype=np.int32)
+    rc = lib.pq_sampler_draw_c128(
+        U.ctypes.data_as(_lib.c_double_p), d, oo.shape[0],
+        oo.ctypes.data_as(_lib.c_int32_p), io.ctypes.data_as(_lib.c_int32_p),
+        u.ctypes.data_as(_lib.c_double_p), index.ctypes.data_as(_lib.c_int32_p))
+    if rc in (_lib.PQ_ERR_BAD_ARG, _lib.PQ_ERR_TOO_LARGE):
+        raise ValueError(_lib.last_error())
+    _lib.check(rc)
+    if (index < 0).any():
+        raise ValueError("probabilities contain NaN")  # numpy's message for such a row
+    TIMERS["  of which GPU kernels (CUDA events)"] = (
+        TIMERS.get("  of which GPU kernels (CUDA events)", 0.0)
+        + max(lib.pq_last_kernel_ms(0), 0.0) * 1e-3)
+    return index
+
+
 def _generate_samples_by_coroutines(input, shots, interferometer, seed_sequence,
                                     reject_condition, postselect_data,
                                     uniform_particle_overlap, pmf_rows):
@@ -255,7 +290,7 @@ def generate_lossy_samples(input, shots, interferometer, seed_sequence, postsele
 
 def generate_samples(input, shots, interferometer, seed_sequence, reject_condition=None,
                      batch_shots=None, postselect_data=None, uniform_particle_overlap=None,
-                     pmf_rows=None):
+                     pmf_rows=None, overlap=1):
     """Clifford & Clifford algorithm B, all shots in lock step.
 
     Restates ``_generate_samples`` / ``_generate_sample`` / ``_calculate_pmf``
@@ -271,8 +306,11 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
     draws are issued here as ``integers(0, len)`` and ``random()`` +
     ``cdf.searchsorted(u, side="right")``, which is what ``Generator.choice``
     does internally and consumes the bit stream identically
-    (``tests/test_host.py::test_numpy_choice_equivalences`` pins that), so the
-    returned tuples are identical to the reference's for the same seed.
+    (``tests/test_host.py::test_numpy_choice_equivalences`` pins that), and both
+    are derived for all shots at once from the shots' raw PCG64 streams
+    (:mod:`piquasso_b200.shot_rng`, pinned against real generators by
+    ``test_shot_streams_replay_numpy_generators``), so the returned tuples are
+    identical to the reference's for the same seed.
 
     ``reject_condition`` (uniform losses, ``simulation_steps.py:350-360``) is a
     state-independent callable the reference evaluates once per photon per shot
@@ -283,36 +321,42 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
     ``uniform_particle_overlap`` select the reference's other per-shot
     algorithms (sampling.py:73-97); those run through the coroutine engine of
     :mod:`piquasso_b200.shot_engine`, still one batched GPU call per round.
-    ``pmf_rows`` replaces :func:`sampler_pmf` (tests inject the oracle there to
-    exercise the host logic without a GPU).
+    ``pmf_rows`` replaces the GPU call (tests inject the oracle there to exercise
+    the host logic without a GPU); without it the plain sampler also draws on the
+    device (:func:`sampler_draw`) and only the chosen modes come back.
+    ``overlap`` > 1 runs unequal shot batches in that many worker threads (host
+    bookkeeping and planning of one batch under the GPU time of another;
+    measured gain on config 4 is a few percent because the GPU time sits in the
+    last three photons, so it is off by default); ``batch_shots`` fixes the batch
+    size instead.  The result does not depend on either.
     """
     import time
 
-    if pmf_rows is None:
-        pmf_rows = sampler_pmf
     if ((postselect_data is not None and len(postselect_data[0]) > 0)
             or uniform_particle_overlap is not None):
         return _generate_samples_by_coroutines(input, shots, interferometer, seed_sequence,
                                                reject_condition, postselect_data,
-                                               uniform_particle_overlap, pmf_rows)
+                                               uniform_particle_overlap,
+                                               pmf_rows or sampler_pmf)
     input = np.asarray(input, dtype=int)
     U = np.ascontiguousarray(interferometer, dtype=np.complex128)
     d = len(input)
     n = int(np.sum(input))
     first_quantized = _to_first_quantized(input)
-    if batch_shots is None:
-        batch_shots = shots
     if reject_condition is None:
         rejected = np.zeros((shots, n), dtype=bool)
     else:
         rejected = np.array([[bool(reject_condition()) for _ in range(n)]
                              for _ in range(shots)], dtype=bool).reshape(shots, n)
-    samples_all = []
     cols = np.arange(max(n, 1))
-    for start in range(0, shots, max(1, batch_shots)):
-        stop = min(shots, start + max(1, batch_shots))
+
+    def run_batch(start, stop):
         nb = stop - start
-        rngs = [np.random.default_rng(seed=seed_sequence + idx) for idx in range(start, stop)]
+        t0 = time.perf_counter()
+        # shot idx owns default_rng(seed_sequence + idx); shot_rng replays numpy's
+        # integers() / random() on the raw streams of all shots at once
+        streams = ShotStreams(seed_sequence, start, stop, draws_per_shot=2 * n + 2)
+        _tick("host: per-shot generators", t0)
         sample = np.zeros((nb, d), dtype=np.int32)
         current_input = np.zeros((nb, d), dtype=np.int32)
         # to_shrink of every shot as rows of one array, `remaining` entries valid
@@ -325,8 +369,7 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
                 continue
             # _grow_current_input (sampling.py:197-205): rng.choice(len(to_shrink)),
             # take that mode, np.delete it (later entries shift left)
-            ridx = np.fromiter((rngs[s].integers(0, remaining[s]) for s in live),
-                               dtype=np.int64, count=live.size)
+            ridx = streams.integers(live, remaining[live])
             modes = shrink[live, ridx]
             current_input[live, modes] += 1
             if n > 1:
@@ -336,17 +379,57 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
             remaining[live] -= 1
             _tick("host: grow input", t0)
             t0 = time.perf_counter()
-            pmf = pmf_rows(U, sample[live], current_input[live])
-            _tick("pq_sampler_pmf_c128 (filter + plan + GPU walk + pmf)", t0)
+            # _sample_from_pmf: Generator.choice(a, p=p) = cdf.searchsorted(random(),
+            # side="right"); the variate does not depend on the pmf, so it is drawn
+            # first and the search can happen next to the pmf, on the device
+            u = streams.random(live)
+            _tick("host: rng.random", t0)
             t0 = time.perf_counter()
-            # _calculate_pmf normalisation (sequential sum) and _sample_from_pmf:
-            # Generator.choice(a, p=p) = cdf.searchsorted(random(), side="right")
-            p = pmf / np.cumsum(pmf, axis=1)[:, -1:]
-            cdf = np.cumsum(p, axis=1)
-            cdf /= cdf[:, -1:]
-            u = np.fromiter((rngs[s].random() for s in live), dtype=np.float64, count=live.size)
-            index = (cdf <= u[:, None]).sum(axis=1)
+            if pmf_rows is None:
+                index = sampler_draw(U, sample[live], current_input[live], u)
+                _tick("pq_sampler_draw_c128 (filter + plan + GPU walk + pmf + draw)", t0)
+            else:
+                pmf = pmf_rows(U, sample[live], current_input[live])
+                _tick("pmf_rows", t0)
+                t0 = time.perf_counter()
+                # _calculate_pmf normalisation (sequential sum), then numpy's choice
+                p = pmf / np.cumsum(pmf, axis=1)[:, -1:]
+                cdf = np.cumsum(p, axis=1)
+                cdf /= cdf[:, -1:]
+                index = (cdf <= u[:, None]).sum(axis=1)
+                _tick("host: normalise + search", t0)
             sample[live, index] += 1
-            _tick("host: normalise + draw", t0)
-        samples_all.extend(tuple(int(x) for x in row) for row in sample)
-    return samples_all
+        return [tuple(row) for row in sample.tolist()]
+
+    # Shots are independent, so batches may run concurrently: while one batch
+    # waits for the GPU inside the library call (GIL released, calls serialised
+    # by the library), another does its host bookkeeping.  Unequal batch sizes
+    # keep the two threads out of step -- one in its host-bound early photons
+    # while the other is in its GPU-bound late ones.
+    bounds = _batch_bounds(shots, batch_shots, overlap if pmf_rows is None else 1)
+    if len(bounds) <= 1 or overlap <= 1 or pmf_rows is not None:
+        parts = [run_batch(b, e) for b, e in bounds]
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=overlap) as pool:
+            parts = list(pool.map(lambda be: run_batch(*be), bounds))
+    return [smp for part in parts for smp in part]
+
+
+# shots below which one batch is not worth splitting for host/GPU overlap
+_OVERLAP_MIN_SHOTS = 2000
+# batch sizes (fractions of the shots) handed to the worker threads in this order
+_OVERLAP_FRACTIONS = (0.375, 0.25, 0.25, 0.125)
+
+
+def _batch_bounds(shots, batch_shots, overlap):
+    """[(begin, end)] of the shot batches of generate_samples."""
+    if batch_shots is not None:
+        step = max(1, int(batch_shots))
+        return [(b, min(shots, b + step)) for b in range(0, shots, step)]
+    if overlap <= 1 or shots < _OVERLAP_MIN_SHOTS:
+        return [(0, shots)] if shots > 0 else []
+    cuts = np.rint(np.cumsum((0.0,) + _OVERLAP_FRACTIONS) * shots).astype(int)
+    cuts[-1] = shots
+    return [(int(b), int(e)) for b, e in zip(cuts[:-1], cuts[1:]) if e > b]
+

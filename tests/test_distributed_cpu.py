@@ -93,10 +93,10 @@ def _sampler_worker(rank, world, port, results):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from piquasso_b200 import distributed, sampling
-    sampling.sampler_pmf = _oracle_sampler_pmf
+    from piquasso_b200 import distributed
     u = haar(6, 3)
-    results[rank] = distributed.generate_samples_sharded([1, 1, 0, 2, 0, 0], 7, u, 11)
+    results[rank] = distributed.generate_samples_sharded([1, 1, 0, 2, 0, 0], 7, u, 11,
+                                                         pmf_rows=_oracle_sampler_pmf)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -110,11 +110,7 @@ def test_sampler_shots_sharded_over_two_ranks():
     manager = mp.get_context("spawn").Manager()
     results = manager.dict()
     mp.spawn(_sampler_worker, args=(world, _free_port(), results), nprocs=world, join=True)
-    saved = sampling.sampler_pmf
-    sampling.sampler_pmf = _oracle_sampler_pmf
-    try:
-        want = sampling.generate_samples([1, 1, 0, 2, 0, 0], 7, haar(6, 3), 11)
-    finally:
-        sampling.sampler_pmf = saved
+    want = sampling.generate_samples([1, 1, 0, 2, 0, 0], 7, haar(6, 3), 11,
+                                     pmf_rows=_oracle_sampler_pmf)
     assert results[0] == want and results[1] == want
     assert len(want) == 7 and all(sum(s) == 4 for s in want)

@@ -555,3 +555,44 @@ def test_sampler_variant_goldens_identical_samples():
     for case in load_golden("sampler_variants.json"):
         got = run_sampler_variant(case)
         assert [list(s) for s in got] == case["samples"], case["label"]
+
+
+def test_sampler_draw_equals_numpy_choice_on_the_pmf_rows():
+    """pq_sampler_draw_c128 (normalisation + numpy's cdf search on the device) picks,
+    for every shot, exactly the mode the host picks from pq_sampler_pmf_c128's row
+    with the same uniform variate -- including variates at the cdf's own values."""
+    from piquasso_b200.sampling import sampler_draw, sampler_pmf
+    rng = np.random.default_rng(5)
+    d = 12
+    u = haar(d, 12)
+    outs, ins = [], []
+    for trial in range(400):
+        k = int(rng.integers(1, 9))
+        ins.append(rng.multinomial(k, np.ones(d) / d))
+        outs.append(rng.multinomial(k - 1, np.ones(d) / d) if k > 1 else np.zeros(d, int))
+    outs, ins = np.array(outs), np.array(ins)
+    pmf = sampler_pmf(u, outs, ins)
+    p = pmf / np.cumsum(pmf, axis=1)[:, -1:]
+    cdf = np.cumsum(p, axis=1)
+    cdf /= cdf[:, -1:]
+    variates = rng.random(len(outs))
+    variates[:100] = cdf[np.arange(100), rng.integers(0, d - 1, 100)]  # exactly on a step
+    variates[100] = 0.0
+    variates[101] = np.nextafter(1.0, 0.0)
+    want = (cdf <= variates[:, None]).sum(axis=1)
+    for i in range(len(outs)):  # what Generator.choice does with that variate
+        assert want[i] == cdf[i].searchsorted(variates[i], side="right")
+    got = sampler_draw(u, outs, ins, variates)
+    assert np.array_equal(got, want)
+
+
+def test_sampler_overlapping_batches_give_the_same_samples():
+    """Shot batches run by concurrent worker threads (host bookkeeping of one under
+    the GPU time of another) return the single-batch sample list."""
+    from piquasso_b200.sampling import generate_samples
+    d, n, seed = 30, 8, 21
+    u = haar(d, 30)
+    inp = np.array([1] * n + [0] * (d - n))
+    want = generate_samples(inp, 23, u, seed, overlap=1)
+    assert generate_samples(inp, 23, u, seed, batch_shots=5, overlap=3) == want
+    assert generate_samples(inp, 23, u, seed, batch_shots=4, overlap=2) == want

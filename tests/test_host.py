@@ -271,3 +271,34 @@ def test_expanded_interferometer_embeds_the_lossy_matrix_isometrically():
     # (the reference's [[S, C], [C, S]] middle factor is not unitary as a whole)
     left = big[:, :5]
     assert np.allclose(left.conj().T @ left, np.eye(5), atol=1e-12)
+
+
+def test_shot_streams_replay_numpy_generators():
+    """piquasso_b200.shot_rng.ShotStreams derives random() and integers(0, high)
+    from the raw PCG64 stream exactly as numpy's Generator does, for any
+    interleaving (32-bit half buffering), for high == 1 (no draw), through the
+    Lemire rejection loop (large bounds) and past the pre-drawn chunk."""
+    from piquasso_b200.shot_rng import ShotStreams
+    nshots, seed0 = 300, 1234
+    streams = ShotStreams(seed0, 5, 5 + nshots, draws_per_shot=6)
+    gens = [np.random.default_rng(seed0 + idx) for idx in range(5, 5 + nshots)]
+    plan = np.random.default_rng(0)
+    everyone = np.arange(nshots)
+    for step in range(60):
+        live = everyone if step % 3 else np.flatnonzero(plan.random(nshots) < 0.7)
+        kind = plan.integers(0, 4)
+        if kind == 0:
+            want = np.array([gens[s].random() for s in live])
+            assert np.array_equal(streams.random(live), want)
+        elif kind == 1:   # the sampler's bounds
+            high = plan.integers(1, 27, size=live.size)
+            want = np.array([gens[s].integers(0, h) for s, h in zip(live, high)])
+            assert np.array_equal(streams.integers(live, high), want)
+        elif kind == 2:   # bounds where Lemire's rejection actually triggers
+            high = plan.choice([3 << 30, (1 << 32) - 1, (1 << 31) + 12345, 1 << 32, 1],
+                               size=live.size)
+            want = np.array([gens[s].integers(0, h) for s, h in zip(live, high)])
+            assert np.array_equal(streams.integers(live, high), want)
+        else:             # choice(n) is integers(0, n)
+            want = np.array([gens[s].choice(13) for s in live])
+            assert np.array_equal(streams.integers(live, 13), want)

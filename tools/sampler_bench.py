@@ -6,14 +6,21 @@ import numpy as np
 from scipy.stats import unitary_group
 from piquasso_b200 import _lib, sampling
 
-shots = int(sys.argv[1]); d = int(sys.argv[2]) if len(sys.argv) > 2 else 100; n = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+shots = int(pos[0]); d = int(pos[1]) if len(pos) > 1 else 100; n = int(pos[2]) if len(pos) > 2 else 25
 U = unitary_group.rvs(d, random_state=d)
 inp = np.array([1] * n + [0] * (d - n))
 lib = _lib.load()
+kw = {}
+for a in sys.argv:
+    if a.startswith("--fractions="):   # batch sizes handed to the overlap threads
+        sampling._OVERLAP_FRACTIONS = tuple(float(x) for x in a.split("=")[1].split(","))
+    if a.startswith("--overlap="):     # worker threads (1 = single batch, no overlap)
+        kw["overlap"] = int(a.split("=")[1])
 sampling.generate_samples(inp[:], 2, U, 123)  # warm-up
 sampling.TIMERS.clear()
 t = time.perf_counter()
-samples = sampling.generate_samples(inp, shots, U, 123)
+samples = sampling.generate_samples(inp, shots, U, 123, **kw)
 dt = time.perf_counter() - t
 print(f"{shots} shots, {d} modes, {n} photons: {dt:.2f} s  ({dt/shots*1e3:.2f} ms/shot)", flush=True)
 for k, v in sampling.TIMERS.items():
