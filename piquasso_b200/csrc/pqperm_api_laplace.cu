@@ -10,7 +10,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pqperm_ctx.h"
@@ -27,6 +29,10 @@ namespace {
 constexpr int kLapSegLen = 64;
 constexpr int kLapSegLenBig = kLapMaxSegLen;          // 256
 constexpr long long kLapBigProblem = 1LL << 18;       // terms
+// the sampler step plans its shots on up to this many host threads ...
+constexpr int kPlanThreadsMax = 8;
+// ... as long as every thread gets at least this many shots
+constexpr int kPlanShotsPerThread = 1024;
 
 // What the lean planner extracts from one problem's multiplicity vectors
 // (zeros allowed).  Restates src/permanent_laplace.cpp:49-118 of the reference
@@ -426,55 +432,106 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
             return rc0 ? rc0 : fail(PQ_ERR_NO_DEVICE, "no usable CUDA device");
         }
     }
-    std::vector<double> trivial_row(pmf ? 0 : d);
+    // Shots are planned independently: with thousands of them the range is cut
+    // over a few host threads, each filling its own buckets, merged in shot order.
+    struct Part {
+        Buckets buckets;
+        int rc = PQ_OK;
+        std::string err;
+        bool any = false;
+    };
+    auto plan_range = [&](int begin, int end, Buckets &buckets, Part &part) {
+        std::vector<double> trivial_row(pmf ? 0 : d);
+        LapShape sh;
+        for (int s = begin; s < end; s++) {
+            const int32_t *oo = out_occ + (size_t)s * d, *io = in_occ + (size_t)s * d;
+            // The shape is taken from the UNFILTERED occupations: dropping the zeros
+            // first (_filter_zeros, sampling.py:711-720) keeps the order of the
+            // remaining modes, so the same row is pinned and the same digits result.
+            part.rc = lap_shape(d, d, oo, io, sh, part.err);
+            if (part.rc)
+                return;
+            double *prow = pmf ? pmf + (size_t)s * d : trivial_row.data();
+            if (sh.trivial) {
+                // permanent_laplace returns [1] (src/permanent_laplace.cpp:52-57) and
+                // _calculate_pmf then uses the first non-zero input mode only
+                int j = -1;
+                for (int m = 0; m < d && j < 0; m++)
+                    if (io[m] > 0)
+                        j = m;
+                for (int m = 0; m < d; m++) {
+                    double v = 0.0;
+                    if (j >= 0) {
+                        const double w = (double)io[j];
+                        const double re = w * U[((size_t)m * d + j) * 2];
+                        const double im = w * U[((size_t)m * d + j) * 2 + 1];
+                        v = re * re + im * im;
+                    }
+                    prow[m] = v;
+                }
+                if (!pmf)
+                    index[s] = draw_from_row(prow, d, u[s]);
+                continue;
+            }
+            const LapVariant v = laplace_variant(sh.NC);
+            Bucket &bk = buckets.get(v, sh.unit);
+            LapProblem q;
+            lap_fill(sh, v.S * v.NCL, q);
+            q.tag = s;
+            q.rowmode[0] = (uint16_t)sh.pinned;
+            for (int k = 0; k < sh.D; k++)
+                q.rowmode[k + 1] = (uint16_t)sh.src_row[k];
+            for (int k = 0; k < sh.NC; k++)
+                q.colmode[k] = (uint16_t)sh.src_col[k];
+            bk.max_D = std::max(bk.max_D, sh.D);
+            bk.probs.push_back(q);
+            part.any = true;
+        }
+    };
     int rc = PQ_OK;
-    std::string err;
-    LapShape sh;
     g_buckets.reset();
     bool any = false;
-    for (int s = 0; s < nshots; s++) {
-        const int32_t *oo = out_occ + (size_t)s * d, *io = in_occ + (size_t)s * d;
-        // The shape is taken from the UNFILTERED occupations: dropping the zeros
-        // first (_filter_zeros, sampling.py:711-720) keeps the order of the
-        // remaining modes, so the same row is pinned and the same digits result.
-        rc = lap_shape(d, d, oo, io, sh, err);
-        if (rc)
-            return fail(rc, err);
-        double *prow = pmf ? pmf + (size_t)s * d : trivial_row.data();
-        if (sh.trivial) {
-            // permanent_laplace returns [1] (src/permanent_laplace.cpp:52-57) and
-            // _calculate_pmf then uses the first non-zero input mode only
-            int j = -1;
-            for (int m = 0; m < d && j < 0; m++)
-                if (io[m] > 0)
-                    j = m;
-            for (int m = 0; m < d; m++) {
-                double v = 0.0;
-                if (j >= 0) {
-                    const double w = (double)io[j];
-                    const double re = w * U[((size_t)m * d + j) * 2];
-                    const double im = w * U[((size_t)m * d + j) * 2 + 1];
-                    v = re * re + im * im;
-                }
-                prow[m] = v;
-            }
-            if (!pmf)
-                index[s] = draw_from_row(prow, d, u[s]);
-            continue;
+    const int nthreads = (int)std::min<long long>(
+        {(long long)kPlanThreadsMax, (long long)nshots / kPlanShotsPerThread,
+         (long long)std::max(1u, std::thread::hardware_concurrency())});
+    if (nthreads <= 1) {
+        Part part;
+        plan_range(0, nshots, g_buckets, part);
+        if (part.rc)
+            return fail(part.rc, part.err);
+        any = part.any;
+    } else {
+        static thread_local std::vector<Part> parts; // keeps the buckets' capacity
+        if ((int)parts.size() < nthreads)
+            parts.resize(nthreads);
+        std::vector<std::thread> workers;
+        for (int t = 0; t < nthreads; t++) {
+            parts[t].buckets.reset();
+            parts[t].rc = PQ_OK;
+            parts[t].any = false;
+            const int begin = (int)((long long)nshots * t / nthreads);
+            const int end = (int)((long long)nshots * (t + 1) / nthreads);
+            workers.emplace_back(plan_range, begin, end, std::ref(parts[t].buckets),
+                                 std::ref(parts[t]));
         }
-        const LapVariant v = laplace_variant(sh.NC);
-        Bucket &bk = g_buckets.get(v, sh.unit);
-        LapProblem q;
-        lap_fill(sh, v.S * v.NCL, q);
-        q.tag = s;
-        q.rowmode[0] = (uint16_t)sh.pinned;
-        for (int k = 0; k < sh.D; k++)
-            q.rowmode[k + 1] = (uint16_t)sh.src_row[k];
-        for (int k = 0; k < sh.NC; k++)
-            q.colmode[k] = (uint16_t)sh.src_col[k];
-        bk.max_D = std::max(bk.max_D, sh.D);
-        bk.probs.push_back(q);
-        any = true;
+        for (std::thread &w : workers)
+            w.join();
+        for (int t = 0; t < nthreads; t++) {
+            if (parts[t].rc)
+                return fail(parts[t].rc, parts[t].err);
+            any = any || parts[t].any;
+            for (size_t i = 0; i < parts[t].buckets.b.size(); i++) {
+                const Bucket &src = parts[t].buckets.b[i];
+                if (src.probs.empty())
+                    continue;
+                Bucket &dst = g_buckets.b[i];
+                dst.S = src.S;
+                dst.NCL = src.NCL;
+                dst.unit = src.unit;
+                dst.max_D = std::max(dst.max_D, src.max_D);
+                dst.probs.insert(dst.probs.end(), src.probs.begin(), src.probs.end());
+            }
+        }
     }
     if (!any)
         return PQ_OK;

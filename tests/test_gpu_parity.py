@@ -596,3 +596,23 @@ def test_sampler_overlapping_batches_give_the_same_samples():
     want = generate_samples(inp, 23, u, seed, overlap=1)
     assert generate_samples(inp, 23, u, seed, batch_shots=5, overlap=3) == want
     assert generate_samples(inp, 23, u, seed, batch_shots=4, overlap=2) == want
+
+
+def test_sampler_step_planned_on_several_host_threads():
+    """Thousands of shots per photon step are planned on several host threads
+    (merged in shot order): same rows and draws as the same shots in small calls."""
+    from piquasso_b200.sampling import sampler_draw, sampler_pmf
+    rng = np.random.default_rng(11)
+    d, nshots = 10, 5000
+    u = haar(d, 10)
+    k = rng.integers(1, 7, size=nshots)
+    ins = np.array([rng.multinomial(kk, np.ones(d) / d) for kk in k])
+    outs = np.array([rng.multinomial(kk - 1, np.ones(d) / d) if kk > 1 else np.zeros(d, int)
+                     for kk in k])
+    variates = rng.random(nshots)
+    big_pmf = sampler_pmf(u, outs, ins)
+    big_draw = sampler_draw(u, outs, ins, variates)
+    for b in range(0, nshots, 1000):  # below the threading threshold
+        sl = slice(b, b + 1000)
+        assert np.array_equal(sampler_pmf(u, outs[sl], ins[sl]), big_pmf[sl])
+        assert np.array_equal(sampler_draw(u, outs[sl], ins[sl], variates[sl]), big_draw[sl])

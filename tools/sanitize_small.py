@@ -6,7 +6,7 @@ from scipy.stats import unitary_group
 import oracle
 from piquasso_b200 import _lib
 from piquasso_b200._math.permanent import permanent, permanent_laplace
-from piquasso_b200.sampling import permanent_batch, sampler_pmf, grad_perm, permanent_laplace_batch
+from piquasso_b200.sampling import permanent_batch, sampler_pmf, sampler_draw, grad_perm, permanent_laplace_batch
 
 lib = _lib.load()
 rng = np.random.default_rng(0)
@@ -34,3 +34,12 @@ sampler_pmf(U, outs, ins)
 permanent_batch(U, rng.multinomial(3, np.ones(8) / 8, size=30), rng.multinomial(3, np.ones(8) / 8, size=30))
 grad_perm(U[:4, :4], [1, 2, 0, 1], [1, 1, 1, 1])
 print("sanitize_small ok, launches:", lib.pq_launch_count())
+
+# device-side draw (pq_sampler_draw_c128), incl. the multi-threaded planner
+Ud = unitary_group.rvs(7, random_state=7)
+kk = rng.integers(1, 6, size=2500)
+ins_ = np.array([rng.multinomial(k, np.ones(7) / 7) for k in kk])
+outs_ = np.array([rng.multinomial(k - 1, np.ones(7) / 7) if k > 1 else np.zeros(7, int) for k in kk])
+idx = sampler_draw(Ud, outs_, ins_, rng.random(2500))
+assert idx.min() >= 0 and idx.max() < 7
+print("sampler_draw ok")
