@@ -278,6 +278,56 @@ def main():
                 postselect=((0,), (1,), 1000), lossy_dilation=True)
     print("sampler variant goldens:", len(variant_cases))
 
+
+    # ---- 3c. sampler-level drop-in (piquasso_b200.integration) --------------------
+    # End-to-end check made HERE, where the reference is importable: whole
+    # PassiveSimulator programs (ideal, uniformly lossy, post-selected, non-uniformly
+    # lossy) give the same Result.samples with the reference's own sampler and with
+    # ours patched in (pmf rows from the oracle: the host logic is what is checked).
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from conftest import oracle_pmf_rows
+    from piquasso_b200 import integration
+
+    def programs():
+        U = _ug.rvs(5, random_state=55)
+        with pq.Program() as ideal:
+            pq.Q(all) | pq.NumberState([2, 1, 1, 0, 1])
+            pq.Q(all) | pq.Interferometer(U)
+            pq.Q(all) | pq.ParticleNumberMeasurement()
+        with pq.Program() as uniform_loss:
+            pq.Q(all) | pq.NumberState([1, 1, 1, 1, 0])
+            pq.Q(all) | pq.Interferometer(U)
+            for i in range(5):
+                pq.Q(i) | pq.Loss(transmissivity=0.9)
+            pq.Q(all) | pq.ParticleNumberMeasurement()
+        with pq.Program() as general_loss:
+            pq.Q(all) | pq.NumberState([1, 1, 1, 0, 0])
+            pq.Q(all) | pq.Interferometer(U)
+            pq.Q(0) | pq.Loss(transmissivity=0.4)
+            pq.Q(1) | pq.Loss(transmissivity=0.5)
+            pq.Q(all) | pq.ParticleNumberMeasurement()
+        with pq.Program() as postselected:
+            pq.Q(all) | pq.NumberState([1, 1, 1, 1, 0])
+            pq.Q(all) | pq.Interferometer(U)
+            pq.Q(2) | pq.PostSelectPhotons(photon_counts=(1,))
+            pq.Q(all) | pq.ParticleNumberMeasurement()
+        return {"ideal": ideal, "uniform loss": uniform_loss, "general loss": general_loss,
+                "postselected": postselected}
+
+    def run_all():
+        out = {}
+        for label, program in programs().items():
+            simulator = pq.PassiveSimulator(d=5, config=pq.Config(seed_sequence=77))
+            out[label] = simulator.execute(program, shots=25).samples
+        return out
+
+    stock = run_all()
+    with integration.install(pmf_rows=oracle_pmf_rows):
+        patched = run_all()
+    for label in stock:
+        assert stock[label] == patched[label], ("sampler drop-in differs", label)
+    print("sampler-level drop-in: identical Result.samples for", sorted(stock))
+
     # ---- 4. seeded Haar cases against the compiled reference ---------------------
     from scipy.stats import unitary_group
     rng = np.random.default_rng(2024)

@@ -302,3 +302,44 @@ def test_shot_streams_replay_numpy_generators():
         else:             # choice(n) is integers(0, n)
             want = np.array([gens[s].choice(13) for s in live])
             assert np.array_equal(streams.integers(live, 13), want)
+
+
+def test_sampler_level_dropin_adapters():
+    """piquasso_b200.integration: the adapters keep the reference's signatures
+    (sampling.py:33-42, 110-117), recognise its `lambda: False`, and install()
+    swaps / restores both bindings.  (Whole-simulator equality with the reference
+    is asserted where the reference is importable: tests/golden/make_golden.py 3c.)"""
+    from types import SimpleNamespace
+    from conftest import golden_matrix, load_golden, oracle_pmf_rows
+    from piquasso_b200 import integration
+
+    assert integration._never_rejects(None)
+    assert integration._never_rejects(lambda: False)
+    shared = np.random.default_rng(0)
+    assert not integration._never_rejects(lambda: shared.uniform() > 0.5)
+    assert not integration._never_rejects(lambda: True)
+
+    def stock_generate_samples(*a, **k):
+        raise AssertionError("the stock sampler must not run while patched")
+
+    fake_sampling = SimpleNamespace(generate_samples=stock_generate_samples,
+                                    generate_lossy_samples=stock_generate_samples)
+    fake_steps = SimpleNamespace(generate_samples=stock_generate_samples, unrelated=1)
+    case = next(c for c in load_golden("sampler_variants.json")
+                if c["label"] == "postselect one mode")
+    config = SimpleNamespace(seed_sequence=case["seed_sequence"], use_dask=False)
+    postselect = (tuple(case["postselect_modes"]), tuple(case["postselect_photons"]),
+                  case["max_trials"])
+    with integration.install(modules=[fake_sampling, fake_steps], pmf_rows=oracle_pmf_rows):
+        got = fake_steps.generate_samples(
+            input=np.array(case["input"]), shots=case["shots"],
+            calculate_permanent_laplace=None,
+            interferometer=golden_matrix(case["interferometer"]),
+            reject_condition=lambda: False, postselect_data=postselect,
+            uniform_particle_overlap=None, config=config)
+        assert fake_sampling.generate_lossy_samples is not stock_generate_samples
+    assert [list(s) for s in got] == case["samples"]
+    assert fake_steps.generate_samples is stock_generate_samples
+    assert fake_sampling.generate_lossy_samples is stock_generate_samples
+    with pytest.raises(ImportError):
+        integration.install(modules=[SimpleNamespace()])
