@@ -76,6 +76,22 @@ int pq_perm_laplace_c64(const float *A, int R, int C, const int32_t *rows,
                         const int32_t *cols, float *out, int *out_len);
 
 /* ---------------------------------------------------------------------
+ * One LARGE permanent_laplace over several GPUs (the
+ * term-space split of a single Laplace call): rank `part` of `nparts` walks the
+ * contiguous share [nseg*part/nparts, nseg*(part+1)/nparts) of the problem's
+ * Gray-code segments -- the rule of src/permanent.cpp:158-164 applied to
+ * permanent_laplace_cpp's loop (src/permanent_laplace.cpp:120-134) -- and
+ * returns its partial sums, already scaled by 2^-(sum_rows-1), in the layout of
+ * pq_perm_laplace_c128.  The results of all parts add up to
+ * permanent_laplace(A, rows, cols); the exchange step is one sum (all-gather +
+ * add, or all-reduce) of C complex numbers per rank.  On the reference's
+ * early-out part 0 returns [1] and the others [0].
+ * ------------------------------------------------------------------- */
+int pq_perm_laplace_partial_c128(const double *A, int R, int C, const int32_t *rows,
+                                 const int32_t *cols, int part, int nparts, double *out,
+                                 int *out_len);
+
+/* ---------------------------------------------------------------------
  * Batch of independent permanent_laplace problems in one call (what the
  * Clifford-Clifford sampler issues once per photon per shot,
  * piquasso/_simulators/passive/sampling.py:723-734).  Problem b has

@@ -303,10 +303,12 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
     return PQ_OK;
 }
 
+// part / nparts: walk only this rank's contiguous share of every problem's
+// segments (results are then partial sums, already scaled by 2^-(sum_rows-1)).
 int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const int32_t *R,
                          const int32_t *C, const int32_t *rows, const int64_t *r_off,
                          const int32_t *cols, const int64_t *c_off, double *out,
-                         const int64_t *o_off, int32_t *out_len)
+                         const int64_t *o_off, int32_t *out_len, int part = 0, int nparts = 1)
 {
     std::string err;
     LapShape sh;
@@ -320,7 +322,7 @@ int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const
         if (rc)
             return fail(rc, err);
         if (sh.trivial) {
-            out[2 * o_off[b]] = 1.0;
+            out[2 * o_off[b]] = part == 0 ? 1.0 : 0.0; // the parts sum to the early-out [1]
             out[2 * o_off[b] + 1] = 0.0;
             out_len[b] = 1;
             continue;
@@ -331,6 +333,12 @@ int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const
         const int NCP = v.S * v.NCL;
         LapProblem q;
         lap_fill(sh, NCP, q);
+        if (nparts > 1) {
+            const long long lo = (long long)(((__int128)q.nseg * part) / nparts);
+            const long long hi = (long long)(((__int128)q.nseg * (part + 1)) / nparts);
+            q.seg_begin = lo;
+            q.nseg = hi - lo;
+        }
         q.tag = b;
         q.a_off = (long long)(bk.a2.size() / 2);
         // compacted, pre-doubled matrix: row 0 = pinned row, rows 1..D = 2 a_d
@@ -700,6 +708,26 @@ extern "C" int pq_perm_laplace_c128(const double *A, int R, int C, const int32_t
     int32_t len = 0;
     const int rc = pq_perm_laplace_batch_c128(1, A, &zero, &r32, &c32, rows, &zero, cols, &zero,
                                               out, &zero, &len);
+    if (rc)
+        return rc;
+    *out_len = len;
+    return PQ_OK;
+}
+
+extern "C" int pq_perm_laplace_partial_c128(const double *A, int R, int C, const int32_t *rows,
+                                            const int32_t *cols, int part, int nparts,
+                                            double *out, int *out_len)
+{
+    if (!out || !out_len || (R > 0 && C > 0 && !A))
+        return fail(PQ_ERR_BAD_ARG, "null pointer");
+    if (R < 0 || C < 0 || nparts < 1 || part < 0 || part >= nparts)
+        return fail(PQ_ERR_BAD_ARG, "bad shape or part index");
+    const int64_t zero = 0;
+    const int32_t r32 = R, c32 = C;
+    int32_t len = 0;
+    std::lock_guard<std::mutex> lock(g_mu);
+    const int rc = laplace_batch_locked(1, A, &zero, &r32, &c32, rows, &zero, cols, &zero, out,
+                                        &zero, &len, part, nparts);
     if (rc)
         return rc;
     *out_len = len;

@@ -35,7 +35,8 @@ struct WalkParams {
 
 struct LapProblem {
     long long a_off;     // first double2 of this problem's (D+1) x NCP matrix in the pack
-    long long nseg;      // Gray segments
+    long long nseg;      // Gray segments walked by this launch ...
+    long long seg_begin; // ... starting at this one (term-space split over ranks)
     int first_block;     // CTAs [first_block, first_block + nblocks) work on this problem
     int nblocks;
     int D;               // Gray digits

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                           threadIdx.x / S;
          seg0 - group_in_warp < Q.nseg; seg0 += gstride) {
         const bool valid = seg0 < Q.nseg;
-        const long long seg = valid ? seg0 : Q.nseg - 1;
+        const long long seg = Q.seg_begin + (valid ? seg0 : Q.nseg - 1);
         // ---- seed (same bookkeeping as seed_segment in pqperm_walk.cuh)
         double sr[NCL], si[NCL];
 #pragma unroll

@@ -97,6 +97,58 @@ def permanent_allgather(matrix, rows, cols, group=None, device_index=None):
     return np.array(np.complex128(finish(total, int(r.sum()))))
 
 
+def _laplace_device_partial(a, r, c, part, nparts):
+    """This rank's share of one permanent_laplace problem (pq_perm_laplace_partial_c128):
+    complex128 array of length C, or 1 on the reference's early-out."""
+    lib = _lib.load()
+    out = np.zeros(2 * max(a.shape[1], 1))
+    out_len = ctypes.c_int(0)
+    rc = lib.pq_perm_laplace_partial_c128(
+        a.ctypes.data_as(_lib.c_double_p), a.shape[0], a.shape[1],
+        r.ctypes.data_as(_lib.c_int32_p), c.ctypes.data_as(_lib.c_int32_p),
+        part, nparts, out.ctypes.data_as(_lib.c_double_p), ctypes.byref(out_len))
+    _raise(rc)
+    return out[: 2 * out_len.value].view(np.complex128).copy()
+
+
+def permanent_laplace_allgather(matrix, rows, cols, group=None, device_index=None):
+    """``permanent_laplace(matrix, rows, cols)`` of ONE large problem computed by
+    all ranks of ``group`` together: rank g walks the
+    contiguous share ``[nseg*g//G, nseg*(g+1)//G)`` of the problem's Gray-code
+    segments, and the only exchange step is one all-gather of C complex numbers per
+    rank, summed by every rank in rank order (identical result on all ranks).
+
+    Batches of small problems (the sampler) shard by problem instead
+    (:func:`generate_samples_sharded`).  Must be called by all ranks with
+    identical arguments."""
+    import torch
+    import torch.distributed as dist
+
+    a = np.ascontiguousarray(_resolve_matrix(matrix), dtype=np.complex128)
+    r = _resolve_mult(rows, "rows")
+    c = _resolve_mult(cols, "cols")
+    _check_shapes(a, r, c)
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    mine = _laplace_device_partial(a, r, c, rank, world)
+    if world == 1:
+        return mine
+    local = torch.from_numpy(np.ascontiguousarray(mine.view(np.float64)))
+    if dist.get_backend(group) == "nccl":
+        if device_index is None:
+            device_index = torch.cuda.current_device()
+        local = local.to("cuda:%d" % device_index)
+    gathered = torch.empty(world * local.numel(), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, local, group=group)
+    parts = gathered.cpu().numpy().reshape(world, -1)
+    total = np.zeros(parts.shape[1])
+    for g in range(world):  # fixed order: every rank adds the same numbers the same way
+        total = total + parts[g]
+    return total.view(np.complex128).copy()
+
+
 def generate_samples_sharded(input, shots, interferometer, seed_sequence,
                              reject_condition=None, group=None, pmf_rows=None):
     """The lock-step sampler with the SHOTS sharded over the ranks of ``group``.

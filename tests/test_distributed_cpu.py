@@ -114,3 +114,48 @@ def test_sampler_shots_sharded_over_two_ranks():
                                      pmf_rows=_oracle_sampler_pmf)
     assert results[0] == want and results[1] == want
     assert len(want) == 7 and all(sum(s) == 4 for s in want)
+
+
+def _oracle_laplace_partial(a, r, c, part, nparts):
+    """Stand-in for pq_perm_laplace_partial_c128 on CPU ranks: the oracle's walk of
+    this rank's contiguous share of the term space, scaled like the library's."""
+    if a.shape[0] == 0 or a.shape[1] == 0 or r.sum() == 0 or c.sum() == 0:
+        return np.array([1.0 + 0j if part == 0 else 0j])
+    _, _, idx_max = oracle.partial(a, r, c, 0, 0, laplace=True)
+    b, e = (idx_max * part) // nparts, (idx_max * (part + 1)) // nparts
+    vals, _, _ = oracle.partial(a, r, c, b, e, laplace=True)
+    return vals / 2.0 ** (int(r.sum()) - 1)
+
+
+def _laplace_worker(rank, world, port, cases, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from piquasso_b200 import distributed
+    distributed._laplace_device_partial = _oracle_laplace_partial
+    results[rank] = [distributed.permanent_laplace_allgather(a, rows, cols) for a, rows, cols in cases]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_ranks_gloo_sum_to_one_permanent_laplace():
+    """One Laplace problem, term space split over two ranks, one all-gather of C
+    complex numbers and a fixed-order sum: both ranks hold permanent_laplace."""
+    rng = np.random.default_rng(9)
+    cases = []
+    for k, rows in ((9, np.ones(8, np.int32)), (7, np.array([2, 1, 3], np.int32)),
+                    (5, np.array([1, 0, 2, 1], np.int32))):
+        a = (rng.normal(size=(len(rows), k)) + 1j * rng.normal(size=(len(rows), k))) / 2
+        cases.append((a, rows, np.ones(k, np.int32)))
+    cases.append((haar(3, 1), np.zeros(3, np.int32), np.ones(3, np.int32)))  # early-out [1]
+    world = 2
+    manager = mp.get_context("spawn").Manager()
+    results = manager.dict()
+    mp.spawn(_laplace_worker, args=(world, _free_port(), cases, results), nprocs=world, join=True)
+    for i, (a, rows, cols) in enumerate(cases):
+        want = oracle.permanent_laplace(a, rows, cols, precision=1)
+        for rank in range(world):
+            assert results[rank][i].shape == want.shape
+            assert np.allclose(results[rank][i], want, rtol=1e-12, atol=1e-14), (i, rank)
+        assert np.array_equal(results[0][i], results[1][i])

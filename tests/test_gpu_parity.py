@@ -616,3 +616,26 @@ def test_sampler_step_planned_on_several_host_threads():
         sl = slice(b, b + 1000)
         assert np.array_equal(sampler_pmf(u, outs[sl], ins[sl]), big_pmf[sl])
         assert np.array_equal(sampler_draw(u, outs[sl], ins[sl], variates[sl]), big_draw[sl])
+
+
+def test_laplace_parts_of_all_ranks_sum_to_the_whole(lib):
+    """pq_perm_laplace_partial_c128: the term-space split of ONE permanent_laplace
+    problem; the parts of 1, 3 and 8 ranks add up to the single call,
+    n-ary rows and zero-multiplicity columns included."""
+    from piquasso_b200.distributed import _laplace_device_partial
+    rng = np.random.default_rng(17)
+    cases = [(np.ones(19, np.int32), np.ones(20, np.int32)),
+             (np.array([3, 2, 4, 1, 2], np.int32), np.ones(13, np.int32)),
+             (np.array([2, 0, 3, 1], np.int32), np.array([2, 0, 1, 3, 1], np.int32))]
+    for rows, cols in cases:
+        a = (rng.normal(size=(len(rows), len(cols))) + 1j * rng.normal(size=(len(rows), len(cols)))) / 2
+        whole = permanent_laplace(a, rows, cols)
+        want = oracle.permanent_laplace(a, rows, cols, precision=1)
+        assert np.allclose(whole, want, rtol=RTOL, atol=1e-13)
+        for nparts in (1, 3, 8):
+            total = sum(_laplace_device_partial(a, rows, cols, g, nparts) for g in range(nparts))
+            assert np.allclose(total, want, rtol=RTOL, atol=1e-13), (rows, nparts)
+    a = haar(3, 3)
+    parts = [_laplace_device_partial(a, np.zeros(3, np.int32), np.ones(3, np.int32), g, 2)
+             for g in range(2)]
+    assert [p.tolist() for p in parts] == [[1.0 + 0j], [0j]]

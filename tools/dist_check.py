@@ -31,5 +31,20 @@ exact = math.factorial(n) * np.prod(u) * np.prod(w)
 got = complex(permanent_allgather(np.outer(u, w), np.ones(n, np.int32), np.ones(n, np.int32), device_index=local))
 e = abs(got - exact) / abs(exact); ok &= e < 1e-10
 if rank == 0: print(f"rank-1 n=34 world={world} relerr vs closed form {e:.2e}; ALL OK = {ok}", flush=True)
+# one large permanent_laplace, term space split over the ranks
+import time
+from piquasso_b200._math.permanent import permanent_laplace
+from piquasso_b200.distributed import permanent_laplace_allgather
+for k in (16, 29):
+    A = np.ascontiguousarray(unitary_group.rvs(k + 3, random_state=k)[: k - 1, :k])
+    r = np.ones(k - 1, np.int32); c = np.ones(k, np.int32)
+    permanent_laplace_allgather(A, r, c, device_index=local)
+    dist.barrier(); t = time.perf_counter()
+    got = permanent_laplace_allgather(A, r, c, device_index=local)
+    dist.barrier(); dt = time.perf_counter() - t
+    t = time.perf_counter(); want = permanent_laplace(A, r, c); dt1 = time.perf_counter() - t
+    e = float(np.max(np.abs(got - want) / np.abs(want))); ok &= e < 1e-11
+    if rank == 0: print(f"laplace k={k} world={world}: {dt*1e3:.2f} ms vs {dt1*1e3:.2f} ms on one GPU, max relerr {e:.2e}", flush=True)
+if rank == 0: print(f"ALL OK (incl. laplace) = {ok}", flush=True)
 dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if ok else 1)
