@@ -147,6 +147,15 @@ int pq_sampler_pmf_c128(const double *U, int d, int nshots, const int32_t *out_o
 int pq_sampler_draw_c128(const double *U, int d, int nshots, const int32_t *out_occ,
                          const int32_t *in_occ, const double *u, int32_t *index);
 
+/* The same on an explicit CUDA device.  Steps issued by different host threads
+ * for DIFFERENT devices run concurrently (each device has its own lock, scratch
+ * and stream): shots are independent (sampling.py:149-194 gives every shot its
+ * own generator), so a single process shards them over the GPUs of a box with
+ * one thread per device and no exchange step. */
+int pq_sampler_draw_dev_c128(int device, const double *U, int d, int nshots,
+                             const int32_t *out_occ, const int32_t *in_occ, const double *u,
+                             int32_t *index);
+
 /* ---------------------------------------------------------------------
  * Partitioned permanent: the piece of one permanent that rank `part` of
  * `nparts` owns.  The term space [0, idx_max) (src/permanent.cpp:131-142) is

@@ -110,6 +110,8 @@ int ctx_get(int device, DeviceCtx **out)
         PQ_CUDA(cudaEventCreate(&c->ev0));
         PQ_CUDA(cudaEventCreate(&c->ev1));
         PQ_CUDA(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+        PQ_CUDA(cudaEventCreate(&c->lap_ev0));
+        PQ_CUDA(cudaEventCreate(&c->lap_ev1));
         for (int i = 0; i < kTimingRing; i++) {
             PQ_CUDA(cudaEventCreate(&c->ring0[i]));
             PQ_CUDA(cudaEventCreate(&c->ring1[i]));

@@ -232,7 +232,7 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
     P.nprob = n;
     P.perm_only = (epi && epi->perm_only) ? 1 : 0;
     const size_t smem = (size_t)(bk.max_D + 1) * NCP * sizeof(double2);
-    PQ_CUDA(cudaEventRecord(c->ev0, st));
+    PQ_CUDA(cudaEventRecord(c->lap_ev0, st));
     cudaError_t e = launch_laplace(bk.S, bk.NCL, bk.unit, P, total_blocks, smem, st);
     if (e != cudaSuccess)
         return fail_cuda(e, "launch laplace_walk_kernel");
@@ -284,11 +284,11 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
         h_dst = c->h_lap[2];
         d_src = c->d_lap[3];
     }
-    PQ_CUDA(cudaEventRecord(c->ev1, st));
+    PQ_CUDA(cudaEventRecord(c->lap_ev1, st));
     PQ_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
     PQ_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
+    if (cudaEventElapsedTime(&ms, c->lap_ev0, c->lap_ev1) == cudaSuccess)
         c->last_kernel_ms = (c->last_kernel_ms < 0 ? 0.0 : c->last_kernel_ms) + ms;
     if (epi && epi->index) {
         const int32_t *src = reinterpret_cast<const int32_t *>(c->h_lap[1]);
@@ -371,6 +371,7 @@ int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const
     int rc = ctx_get(g_devices[0], &c);
     if (rc)
         return rc;
+    std::lock_guard<std::mutex> dev_lock(c->mu);
     c->last_kernel_ms = -1.0;
     for (Bucket &bk : g_buckets.b) {
         if (bk.probs.empty())
@@ -420,9 +421,10 @@ int draw_from_row(const double *row, int d, double u)
 
 // pmf != nullptr: return the unnormalised pmf rows.  Otherwise draw on the
 // device: index[s] = the output mode numpy's choice would pick for u[s].
+// device < 0: the library's first device (pq_set_devices).
 int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
                  const int32_t *in_occ, double *pmf, const double *u = nullptr,
-                 int32_t *index = nullptr)
+                 int32_t *index = nullptr, int device = -1)
 {
     // Planning (zero filtering, shapes, problem descriptors) touches only the
     // caller's arguments and this thread's buckets: it runs OUTSIDE the library
@@ -543,10 +545,15 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
     }
     if (!any)
         return PQ_OK;
-    std::lock_guard<std::mutex> lock(g_mu);
+    // The device phase holds only this device's lock: steps of other host threads
+    // on other devices run concurrently (single-process multi-GPU sampling).
     DeviceCtx *c = nullptr;
-    if ((rc = ctx_get(g_devices[0], &c)))
-        return rc;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if ((rc = ctx_get(device >= 0 ? device : g_devices[0], &c)))
+            return rc;
+    }
+    std::lock_guard<std::mutex> dev_lock(c->mu);
     const size_t ubytes = (size_t)d * d * sizeof(double2);
     if ((rc = grow_dev(c, 4, ubytes)))
         return rc;
@@ -617,6 +624,7 @@ int perm_batch_locked(const double *U, int R, int C, int nprob, const int32_t *r
     int rc = ctx_get(g_devices[0], &c);
     if (rc)
         return rc;
+    std::lock_guard<std::mutex> dev_lock(c->mu);
     // gather mode needs a square leading dimension only for addressing: ldu = C
     const size_t ubytes = (size_t)R * C * sizeof(double2);
     if ((rc = grow_dev(c, 4, ubytes)))
@@ -679,6 +687,18 @@ extern "C" int pq_sampler_draw_c128(const double *U, int d, int nshots, const in
     if (nshots == 0)
         return PQ_OK;
     return sampler_step(U, d, nshots, out_occ, in_occ, nullptr, u, index);
+}
+
+extern "C" int pq_sampler_draw_dev_c128(int device, const double *U, int d, int nshots,
+                                        const int32_t *out_occ, const int32_t *in_occ,
+                                        const double *u, int32_t *index)
+{
+    if (device < 0 || d < 1 || d > 65535 || nshots < 0 || !U ||
+        (nshots > 0 && (!out_occ || !in_occ || !u || !index)))
+        return fail(PQ_ERR_BAD_ARG, "bad sampler arguments");
+    if (nshots == 0)
+        return PQ_OK;
+    return sampler_step(U, d, nshots, out_occ, in_occ, nullptr, u, index, device);
 }
 
 extern "C" int pq_perm_laplace_batch_c128(int nprob, const double *A, const int64_t *a_off,

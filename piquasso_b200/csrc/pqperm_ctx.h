@@ -40,6 +40,11 @@ struct DeviceCtx {
     uint64_t resident_job = 0;     // id of the pq_perm_job whose inputs sit in the buffers
     cudaEvent_t ring0[kTimingRing], ring1[kTimingRing];  // event pairs around the kernels
     uint64_t ring_next = 0;
+    // The batched Laplace / sampler path: its device phase runs under `mu` (not
+    // under the library-wide g_mu), so that host threads driving DIFFERENT devices
+    // overlap; it touches only the members below plus `stream`.
+    std::mutex mu;
+    cudaEvent_t lap_ev0 = nullptr, lap_ev1 = nullptr;
     // growable scratch of the batched Laplace path
     // prob, A2, partials, out, U, pmf, uniform draws, drawn indices
     void *d_lap[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -120,7 +120,8 @@ def permanent_laplace_allgather(matrix, rows, cols, group=None, device_index=Non
 
     Batches of small problems (the sampler) shard by problem instead
     (:func:`generate_samples_sharded`).  Must be called by all ranks with
-    identical arguments."""
+    identical arguments.  On a GPU box the library's device list is set to this
+    rank's device (``pq_set_devices``), as for every Laplace entry."""
     import torch
     import torch.distributed as dist
 
@@ -132,13 +133,16 @@ def permanent_laplace_allgather(matrix, rows, cols, group=None, device_index=Non
         rank, world = dist.get_rank(group), dist.get_world_size(group)
     else:
         rank, world = 0, 1
+    if torch.cuda.is_available():
+        # the Laplace entries run on the library's first device: make it this rank's
+        if device_index is None:
+            device_index = torch.cuda.current_device()
+        _lib.check(_lib.load().pq_set_devices((ctypes.c_int32 * 1)(device_index), 1))
     mine = _laplace_device_partial(a, r, c, rank, world)
     if world == 1:
         return mine
     local = torch.from_numpy(np.ascontiguousarray(mine.view(np.float64)))
     if dist.get_backend(group) == "nccl":
-        if device_index is None:
-            device_index = torch.cuda.current_device()
         local = local.to("cuda:%d" % device_index)
     gathered = torch.empty(world * local.numel(), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(gathered, local, group=group)

@@ -40,7 +40,7 @@ def _never_rejects(reject_condition):
     return reject_condition() is False
 
 
-def make_adapters(pmf_rows=None):
+def make_adapters(pmf_rows=None, devices=None):
     """(generate_samples, generate_lossy_samples) with the reference's signatures
     (``sampling.py:33-42, 110-117``).  ``calculate_permanent_laplace`` and
     ``config.use_dask`` are ignored: the permanents run batched in libpqperm."""
@@ -52,7 +52,8 @@ def make_adapters(pmf_rows=None):
         return sampling.generate_samples(
             input, shots, interferometer, config.seed_sequence,
             reject_condition=reject_condition, postselect_data=postselect_data,
-            uniform_particle_overlap=uniform_particle_overlap, pmf_rows=pmf_rows)
+            uniform_particle_overlap=uniform_particle_overlap, pmf_rows=pmf_rows,
+            devices=devices)
 
     def generate_lossy_samples(input, shots, calculate_permanent_laplace, interferometer,
                                postselect_data, config):
@@ -80,21 +81,24 @@ class _Handle:
         return False
 
 
-def install(modules=None, pmf_rows=None):
+def install(modules=None, pmf_rows=None, devices=None):
     """Patch piquasso's passive sampler; returns a handle with ``uninstall()``
     (also a context manager).
 
     ``modules`` defaults to ``piquasso._simulators.passive.sampling`` and
     ``...simulation_steps`` (the latter imports the functions by name, so both
     bindings are replaced).  ``pmf_rows`` is passed to
-    :func:`piquasso_b200.sampling.generate_samples` (CPU tests inject the oracle)."""
+    :func:`piquasso_b200.sampling.generate_samples` (CPU tests inject the oracle),
+    and so is ``devices`` (CUDA device indices: the plain sampler shards its shots
+    over them inside this process)."""
     if modules is None:
         try:
             modules = [importlib.import_module("piquasso._simulators.passive.sampling"),
                        importlib.import_module("piquasso._simulators.passive.simulation_steps")]
         except ImportError as exc:
             raise ImportError("piquasso is not importable here; nothing to patch") from exc
-    adapters = dict(zip(("generate_samples", "generate_lossy_samples"), make_adapters(pmf_rows)))
+    adapters = dict(zip(("generate_samples", "generate_lossy_samples"),
+                        make_adapters(pmf_rows, devices)))
     patched = []
     for module in modules:
         for name, adapter in adapters.items():

@@ -199,13 +199,15 @@ def sampler_pmf(interferometer, out_occ, in_occ):
     return pmf
 
 
-def sampler_draw(interferometer, out_occ, in_occ, uniforms):
+def sampler_draw(interferometer, out_occ, in_occ, uniforms, device=None):
     """One photon step including the draw (``pq_sampler_draw_c128``): entry s is
     ``rng.choice(arange(d), p=_calculate_pmf(in_occ[s], out_occ[s], ...))`` of the
     reference (sampling.py:723-753) for the generator state in which
     ``rng.random()`` returns ``uniforms[s]``.  The pmf rows never leave the device:
     normalisation and numpy's cdf search are repeated there operation by
-    operation."""
+    operation.  ``device`` selects a CUDA device explicitly
+    (``pq_sampler_draw_dev_c128``; calls for different devices from different
+    threads run concurrently), ``None`` the library's first device."""
     lib = _lib.load()
     U = np.ascontiguousarray(interferometer, dtype=np.complex128)
     d = U.shape[0]
@@ -217,10 +219,13 @@ def sampler_draw(interferometer, out_occ, in_occ, uniforms):
     if oo.shape != io.shape or u.shape[0] != oo.shape[0]:
         raise ValueError("out_occ, in_occ and uniforms describe different numbers of shots")
     index = np.empty(oo.shape[0], dtype=np.int32)
-    rc = lib.pq_sampler_draw_c128(
-        U.ctypes.data_as(_lib.c_double_p), d, oo.shape[0],
-        oo.ctypes.data_as(_lib.c_int32_p), io.ctypes.data_as(_lib.c_int32_p),
-        u.ctypes.data_as(_lib.c_double_p), index.ctypes.data_as(_lib.c_int32_p))
+    args = (U.ctypes.data_as(_lib.c_double_p), d, oo.shape[0],
+            oo.ctypes.data_as(_lib.c_int32_p), io.ctypes.data_as(_lib.c_int32_p),
+            u.ctypes.data_as(_lib.c_double_p), index.ctypes.data_as(_lib.c_int32_p))
+    if device is None:
+        rc = lib.pq_sampler_draw_c128(*args)
+    else:
+        rc = lib.pq_sampler_draw_dev_c128(int(device), *args)
     if rc in (_lib.PQ_ERR_BAD_ARG, _lib.PQ_ERR_TOO_LARGE):
         raise ValueError(_lib.last_error())
     _lib.check(rc)
@@ -228,7 +233,7 @@ def sampler_draw(interferometer, out_occ, in_occ, uniforms):
         raise ValueError("probabilities contain NaN")  # numpy's message for such a row
     TIMERS["  of which GPU kernels (CUDA events)"] = (
         TIMERS.get("  of which GPU kernels (CUDA events)", 0.0)
-        + max(lib.pq_last_kernel_ms(0), 0.0) * 1e-3)
+        + max(lib.pq_last_kernel_ms(0 if device is None else int(device)), 0.0) * 1e-3)
     return index
 
 
@@ -290,7 +295,7 @@ def generate_lossy_samples(input, shots, interferometer, seed_sequence, postsele
 
 def generate_samples(input, shots, interferometer, seed_sequence, reject_condition=None,
                      batch_shots=None, postselect_data=None, uniform_particle_overlap=None,
-                     pmf_rows=None, overlap=1):
+                     pmf_rows=None, overlap=1, devices=None):
     """Clifford & Clifford algorithm B, all shots in lock step.
 
     Restates ``_generate_samples`` / ``_generate_sample`` / ``_calculate_pmf``
@@ -328,7 +333,9 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
     bookkeeping and planning of one batch under the GPU time of another;
     measured gain on config 4 is a few percent because the GPU time sits in the
     last three photons, so it is off by default); ``batch_shots`` fixes the batch
-    size instead.  The result does not depend on either.
+    size instead.  ``devices`` (CUDA device indices) shards the shots over several
+    GPUs inside this process, one host thread per device.  The result does not
+    depend on any of them.
     """
     import time
 
@@ -350,7 +357,7 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
                              for _ in range(shots)], dtype=bool).reshape(shots, n)
     cols = np.arange(max(n, 1))
 
-    def run_batch(start, stop):
+    def run_batch(start, stop, device=None):
         nb = stop - start
         t0 = time.perf_counter()
         # shot idx owns default_rng(seed_sequence + idx); shot_rng replays numpy's
@@ -386,7 +393,7 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
             _tick("host: rng.random", t0)
             t0 = time.perf_counter()
             if pmf_rows is None:
-                index = sampler_draw(U, sample[live], current_input[live], u)
+                index = sampler_draw(U, sample[live], current_input[live], u, device=device)
                 _tick("pq_sampler_draw_c128 (filter + plan + GPU walk + pmf + draw)", t0)
             else:
                 pmf = pmf_rows(U, sample[live], current_input[live])
@@ -406,13 +413,24 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
     # by the library), another does its host bookkeeping.  Unequal batch sizes
     # keep the two threads out of step -- one in its host-bound early photons
     # while the other is in its GPU-bound late ones.
+    if devices is not None and len(devices) > 1 and pmf_rows is None and shots >= len(devices):
+        # one process, several GPUs: equal contiguous shot ranges, one host thread per
+        # device (the library serialises per device, not globally); no exchange step
+        from concurrent.futures import ThreadPoolExecutor
+        g = len(devices)
+        jobs = [((shots * i) // g, (shots * (i + 1)) // g, int(dev))
+                for i, dev in enumerate(devices)]
+        with ThreadPoolExecutor(max_workers=g) as pool:
+            parts = list(pool.map(lambda job: run_batch(*job), jobs))
+        return [smp for part in parts for smp in part]
+    device = int(devices[0]) if devices is not None and len(devices) == 1 else None
     bounds = _batch_bounds(shots, batch_shots, overlap if pmf_rows is None else 1)
     if len(bounds) <= 1 or overlap <= 1 or pmf_rows is not None:
-        parts = [run_batch(b, e) for b, e in bounds]
+        parts = [run_batch(b, e, device) for b, e in bounds]
     else:
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=overlap) as pool:
-            parts = list(pool.map(lambda be: run_batch(*be), bounds))
+            parts = list(pool.map(lambda be: run_batch(be[0], be[1], device), bounds))
     return [smp for part in parts for smp in part]
 
 

@@ -639,3 +639,18 @@ def test_laplace_parts_of_all_ranks_sum_to_the_whole(lib):
     parts = [_laplace_device_partial(a, np.zeros(3, np.int32), np.ones(3, np.int32), g, 2)
              for g in range(2)]
     assert [p.tolist() for p in parts] == [[1.0 + 0j], [0j]]
+
+
+def test_single_process_sampler_sharded_over_devices(lib):
+    """generate_samples(devices=[...]): one host thread per device through
+    pq_sampler_draw_dev_c128, same sample list as the single-device run.  With one
+    GPU the device is listed twice (two threads, serialised by the device lock)."""
+    from piquasso_b200.sampling import generate_samples
+    d, n, seed = 24, 7, 5
+    u = haar(d, 24)
+    inp = np.array([1] * n + [0] * (d - n))
+    want = generate_samples(inp, 31, u, seed)
+    ndev = lib.pq_device_count()
+    devices = list(range(min(ndev, 4))) if ndev > 1 else [0, 0]
+    assert generate_samples(inp, 31, u, seed, devices=devices) == want
+    assert generate_samples(inp, 31, u, seed, devices=[0]) == want

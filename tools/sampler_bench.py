@@ -17,7 +17,9 @@ for a in sys.argv:
         sampling._OVERLAP_FRACTIONS = tuple(float(x) for x in a.split("=")[1].split(","))
     if a.startswith("--overlap="):     # worker threads (1 = single batch, no overlap)
         kw["overlap"] = int(a.split("=")[1])
-sampling.generate_samples(inp[:], 2, U, 123)  # warm-up
+    if a.startswith("--devices="):     # single process, shots sharded over these GPUs
+        kw["devices"] = [int(x) for x in a.split("=")[1].split(",")]
+sampling.generate_samples(inp[:], 2 * len(kw.get('devices', [0])), U, 123, **kw)  # warm-up
 sampling.TIMERS.clear()
 t = time.perf_counter()
 samples = sampling.generate_samples(inp, shots, U, 123, **kw)
