@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -501,8 +502,14 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
     int rc = PQ_OK;
     g_buckets.reset();
     bool any = false;
+    // PQ_PLAN_THREADS caps the planner threads (1 = plan on the calling thread)
+    static const int thread_cap = [] {
+        const char *env = std::getenv("PQ_PLAN_THREADS");
+        const int v = env ? std::atoi(env) : kPlanThreadsMax;
+        return std::max(1, std::min(v, 64));
+    }();
     const int nthreads = (int)std::min<long long>(
-        {(long long)kPlanThreadsMax, (long long)nshots / kPlanShotsPerThread,
+        {(long long)thread_cap, (long long)nshots / kPlanShotsPerThread,
          (long long)std::max(1u, std::thread::hardware_concurrency())});
     if (nthreads <= 1) {
         Part part;
@@ -543,8 +550,15 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
             }
         }
     }
-    if (!any)
+    if (!any) {
+        // nothing to launch (e.g. the first photon of every shot): no kernel time
+        std::lock_guard<std::mutex> lock(g_mu);
+        DeviceCtx *c0 = nullptr;
+        if ((rc = ctx_get(device >= 0 ? device : g_devices[0], &c0)))
+            return rc;
+        c0->last_kernel_ms = 0.0;
         return PQ_OK;
+    }
     // The device phase holds only this device's lock: steps of other host threads
     // on other devices run concurrently (single-process multi-GPU sampling).
     DeviceCtx *c = nullptr;
