@@ -213,7 +213,13 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
         (rc = grow_dev(c, 3, out_bytes)))
         return rc;
     cudaStream_t st = c->stream;
-    PQ_CUDA(cudaMemcpyAsync(c->d_lap[0], bk.probs.data(), sizeof(LapProblem) * (size_t)n,
+    // descriptors go through pinned staging: a pageable source makes the copy a
+    // driver-staged, host-synchronous one whose cost depends on the state of the
+    // host's pages (megabytes per photon step in the sampler)
+    if ((rc = grow_host(c, 4, sizeof(LapProblem) * (size_t)n)))
+        return rc;
+    std::memcpy(c->h_lap[4], bk.probs.data(), sizeof(LapProblem) * (size_t)n);
+    PQ_CUDA(cudaMemcpyAsync(c->d_lap[0], c->h_lap[4], sizeof(LapProblem) * (size_t)n,
                             cudaMemcpyHostToDevice, st));
     LapParams P;
     std::memset(&P, 0, sizeof(P));

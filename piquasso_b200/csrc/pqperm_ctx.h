@@ -49,9 +49,9 @@ struct DeviceCtx {
     // prob, A2, partials, out, U, pmf, uniform draws, drawn indices
     void *d_lap[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t d_lap_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    // (pinned) uniform draws, drawn indices, out, pmf
-    void *h_lap[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t h_lap_cap[4] = {0, 0, 0, 0};
+    // (pinned) uniform draws, drawn indices, out, pmf, problem descriptors
+    void *h_lap[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t h_lap_cap[5] = {0, 0, 0, 0, 0};
 };
 
 extern std::mutex g_mu;                 // one caller at a time (GIL-held callers anyway)
