@@ -33,10 +33,19 @@ extern "C" {
 #define PQ_ERR_BAD_ARG 2
 #define PQ_ERR_NO_DEVICE 3    /* no CUDA device / driver: there is no CPU fallback */
 #define PQ_ERR_CUDA 4
-#define PQ_ERR_TOO_LARGE 5    /* more than PQ_MAX_COLS active columns or PQ_MAX_DIGITS active rows */
+#define PQ_ERR_TOO_LARGE 5    /* beyond the limits below */
 
-#define PQ_MAX_COLS 64   /* columns with non-zero multiplicity */
-#define PQ_MAX_DIGITS 64 /* rows with non-zero multiplicity after the split */
+/* Limits (the reference has none, but its run time is exponential in the rows):
+ * rows with non-zero multiplicity after the split <= PQ_MAX_DIGITS, multiplicities
+ * <= 254, term space <= 2^62.  Columns with non-zero multiplicity: <= PQ_MAX_COLS
+ * for the partitioned entries (pq_perm_partial_c128, pq_perm_job_*, pq_perm_plan);
+ * <= PQ_MAX_COLS_WIDE for pq_perm_c128 / pq_perm_c64 / pq_perm_batch_c128, the
+ * permanent_laplace entries and the sampler steps -- beyond PQ_MAX_COLS a whole
+ * warp walks each Gray segment, and (active rows + 1) x columns x 16 bytes must
+ * fit in 200 KB of shared memory. */
+#define PQ_MAX_COLS 64
+#define PQ_MAX_COLS_WIDE 256
+#define PQ_MAX_DIGITS 64
 
 /* Message of the last failing call made by this thread ("" if none). */
 const char *pq_last_error(void);

@@ -428,6 +428,15 @@ static int perm_run(const double *A, int R, int C, const int32_t *rows, const in
     if (!out || (R > 0 && C > 0 && !A))
         return fail(PQ_ERR_BAD_ARG, "null pointer");
     std::lock_guard<std::mutex> lock(g_mu);
+    {
+        // more than PQ_MAX_COLS active columns (necessarily few rows): the
+        // warp-per-segment batch walk, which holds up to 256 columns
+        int nc = 0;
+        for (int j = 0; j < C && cols; j++)
+            nc += cols[j] > 0 ? 1 : 0;
+        if (nc > PQ_MAX_COLS && R > 0 && rows)
+            return perm_wide_locked(A, R, C, rows, cols, out);
+    }
     // validate / early-outs first: they need no device, exactly like the reference
     Plan plan;
     std::string err;

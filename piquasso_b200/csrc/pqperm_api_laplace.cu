@@ -46,8 +46,8 @@ struct LapShape {
     bool unit;
     int src_row[kMaxDigits]; // row feeding digit d
     int mult[kMaxDigits];
-    int src_col[kMaxCols];
-    int colmult[kMaxCols];
+    int src_col[kLapMaxCols];
+    int colmult[kLapMaxCols];
 };
 
 int lap_shape(int R, int C, const int32_t *rows, const int32_t *cols, LapShape &sh,
@@ -104,8 +104,8 @@ int lap_shape(int R, int C, const int32_t *rows, const int32_t *cols, LapShape &
     for (int j = 0; j < C; j++) {
         if (cols[j] == 0)
             continue;
-        if (cols[j] > kMaxMultiplicity || sh.NC >= kMaxCols) {
-            err = "more than 64 active columns or a multiplicity above 254";
+        if (cols[j] > kMaxMultiplicity || sh.NC >= kLapMaxCols) {
+            err = "more than 256 active columns or a multiplicity above 254";
             return PQ_ERR_TOO_LARGE;
         }
         sh.src_col[sh.NC] = j;
@@ -120,7 +120,8 @@ int lap_shape(int R, int C, const int32_t *rows, const int32_t *cols, LapShape &
 
 // Fills the walk parameters of a described problem: digits 0..q-1 are walked
 // inside a segment of W <= kLapSegLen terms, the rest index the segments.
-void lap_fill(const LapShape &sh, int ncp, LapProblem &q)
+// Problems wider than kMaxCols keep their column tables in `wide`.
+void lap_fill(const LapShape &sh, int ncp, LapProblem &q, LapWide *wide = nullptr)
 {
     std::memset(&q, 0, sizeof(q));
     q.D = sh.D;
@@ -142,14 +143,33 @@ void lap_fill(const LapShape &sh, int ncp, LapProblem &q)
     q.nseg = total / W;
     q.exp2 = sh.sum_rows - 1;
     q.nc = sh.NC;
-    for (int j = 0; j < ncp; j++)
-        q.colmult[j] = (uint8_t)(j < sh.NC ? sh.colmult[j] : 1);
+    if (wide) {
+        std::memset(wide, 0, sizeof(*wide));
+        for (int j = 0; j < ncp; j++)
+            wide->colmult[j] = (uint8_t)(j < sh.NC ? sh.colmult[j] : 1);
+        for (int j = 0; j < sh.NC; j++)
+            wide->colmode[j] = (uint16_t)sh.src_col[j];
+    } else {
+        for (int j = 0; j < ncp; j++)
+            q.colmult[j] = (uint8_t)(j < sh.NC ? sh.colmult[j] : 1);
+        for (int j = 0; j < sh.NC; j++)
+            q.colmode[j] = (uint16_t)sh.src_col[j];
+    }
 }
+
+// Shared memory of one CTA of the walk for this shape, and the limit it must fit
+// (the (D+1) x NCP matrix is staged per CTA; wide problems with many rows do not).
+constexpr size_t kLapSmemLimit = 200 * 1024;
+const char *const kLapTooWide =
+    "problem too large for the lane-split walk: (active rows + 1) x padded columns x 16 bytes "
+    "exceeds 200 KB of shared memory";
+inline size_t lap_smem_bytes(int D, int ncp) { return (size_t)(D + 1) * ncp * sizeof(double2); }
 
 struct Bucket {
     int S = 0, NCL = 0;
     bool unit = false;
     std::vector<LapProblem> probs;
+    std::vector<LapWide> wide; // S = 32 only: column tables, aligned with probs
     std::vector<double> a2;   // packed mode
     int max_D = 0;
 };
@@ -157,10 +177,10 @@ struct Bucket {
 // buckets[(S index) * 17 * 2 + NCL * 2 + unit]
 struct Buckets {
     std::vector<Bucket> b;
-    Buckets() : b(3 * 17 * 2) {}
+    Buckets() : b(4 * 17 * 2) {}
     Bucket &get(const LapVariant &v, bool unit)
     {
-        const int si = v.S == 1 ? 0 : (v.S == 2 ? 1 : 2);
+        const int si = v.S == 1 ? 0 : (v.S == 2 ? 1 : (v.S == 4 ? 2 : 3));
         Bucket &k = b[(si * 17 + v.NCL) * 2 + (unit ? 1 : 0)];
         k.S = v.S;
         k.NCL = v.NCL;
@@ -171,6 +191,7 @@ struct Buckets {
     {
         for (Bucket &k : b) {
             k.probs.clear();
+            k.wide.clear();
             k.a2.clear();
             k.max_D = 0;
         }
@@ -233,6 +254,13 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
         PQ_CUDA(cudaMemcpyAsync(c->d_lap[1], bk.a2.data(), bk.a2.size() * sizeof(double),
                                 cudaMemcpyHostToDevice, st));
         P.A2 = reinterpret_cast<const double2 *>(c->d_lap[1]);
+    }
+    if (!bk.wide.empty()) {
+        const size_t wbytes = bk.wide.size() * sizeof(LapWide);
+        if ((rc = grow_dev(c, 8, wbytes)))
+            return rc;
+        PQ_CUDA(cudaMemcpyAsync(c->d_lap[8], bk.wide.data(), wbytes, cudaMemcpyHostToDevice, st));
+        P.wide = reinterpret_cast<const LapWide *>(c->d_lap[8]);
     }
     P.partials = reinterpret_cast<double2 *>(c->d_lap[2]);
     P.out = reinterpret_cast<double2 *>(c->d_lap[3]);
@@ -338,8 +366,13 @@ int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const
         const LapVariant v = laplace_variant(sh.NC);
         Bucket &bk = g_buckets.get(v, sh.unit);
         const int NCP = v.S * v.NCL;
+        if (lap_smem_bytes(sh.D, NCP) > kLapSmemLimit)
+            return fail(PQ_ERR_TOO_LARGE, kLapTooWide);
         LapProblem q;
-        lap_fill(sh, NCP, q);
+        LapWide w;
+        lap_fill(sh, NCP, q, v.S == 32 ? &w : nullptr);
+        if (v.S == 32)
+            bk.wide.push_back(w);
         if (nparts > 1) {
             const long long lo = (long long)(((__int128)q.nseg * part) / nparts);
             const long long hi = (long long)(((__int128)q.nseg * (part + 1)) / nparts);
@@ -492,16 +525,22 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
             }
             const LapVariant v = laplace_variant(sh.NC);
             Bucket &bk = buckets.get(v, sh.unit);
+            if (lap_smem_bytes(sh.D, v.S * v.NCL) > kLapSmemLimit) {
+                part.rc = PQ_ERR_TOO_LARGE;
+                part.err = kLapTooWide;
+                return;
+            }
             LapProblem q;
-            lap_fill(sh, v.S * v.NCL, q);
+            LapWide w;
+            lap_fill(sh, v.S * v.NCL, q, v.S == 32 ? &w : nullptr);
             q.tag = s;
             q.rowmode[0] = (uint16_t)sh.pinned;
             for (int k = 0; k < sh.D; k++)
                 q.rowmode[k + 1] = (uint16_t)sh.src_row[k];
-            for (int k = 0; k < sh.NC; k++)
-                q.colmode[k] = (uint16_t)sh.src_col[k];
             bk.max_D = std::max(bk.max_D, sh.D);
             bk.probs.push_back(q);
+            if (v.S == 32)
+                bk.wide.push_back(w);
             part.any = true;
         }
     };
@@ -553,6 +592,7 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
                 dst.unit = src.unit;
                 dst.max_D = std::max(dst.max_D, src.max_D);
                 dst.probs.insert(dst.probs.end(), src.probs.begin(), src.probs.end());
+                dst.wide.insert(dst.wide.end(), src.wide.begin(), src.wide.end());
             }
         }
     }
@@ -626,16 +666,19 @@ int perm_batch_locked(const double *U, int R, int C, int nprob, const int32_t *r
         }
         const LapVariant v = laplace_variant(sh.NC);
         Bucket &bk = g_buckets.get(v, sh.unit);
+        if (lap_smem_bytes(sh.D, v.S * v.NCL) > kLapSmemLimit)
+            return fail(PQ_ERR_TOO_LARGE, kLapTooWide);
         LapProblem q;
-        lap_fill(sh, v.S * v.NCL, q);
+        LapWide w;
+        lap_fill(sh, v.S * v.NCL, q, v.S == 32 ? &w : nullptr);
         q.tag = b;
         q.rowmode[0] = (uint16_t)sh.pinned;
         for (int k = 0; k < sh.D; k++)
             q.rowmode[k + 1] = (uint16_t)sh.src_row[k];
-        for (int k = 0; k < sh.NC; k++)
-            q.colmode[k] = (uint16_t)sh.src_col[k];
         bk.max_D = std::max(bk.max_D, sh.D);
         bk.probs.push_back(q);
+        if (v.S == 32)
+            bk.wide.push_back(w);
         any = true;
     }
     if (!any)
@@ -673,6 +716,14 @@ int perm_batch_locked(const double *U, int R, int C, int nprob, const int32_t *r
 }
 
 } // namespace
+
+namespace pqperm {
+int perm_wide_locked(const double *A, int R, int C, const int32_t *rows, const int32_t *cols,
+                     double out[2])
+{
+    return perm_batch_locked(A, R, C, 1, rows, cols, out);
+}
+} // namespace pqperm
 
 extern "C" int pq_perm_batch_c128(const double *A, int R, int C, int nprob,
                                   const int32_t *row_mult, const int32_t *col_mult,

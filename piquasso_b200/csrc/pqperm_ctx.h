@@ -46,9 +46,10 @@ struct DeviceCtx {
     std::mutex mu;
     cudaEvent_t lap_ev0 = nullptr, lap_ev1 = nullptr;
     // growable scratch of the batched Laplace path
-    // prob, A2, partials, out, U, pmf, uniform draws, drawn indices
-    void *d_lap[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t d_lap_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // prob, A2, partials, out, U, pmf, uniform draws, drawn indices, wide column tables
+    void *d_lap[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                      nullptr};
+    size_t d_lap_cap[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     // (pinned) uniform draws, drawn indices, out, pmf, problem descriptors
     void *h_lap[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t h_lap_cap[5] = {0, 0, 0, 0, 0};
@@ -73,6 +74,11 @@ int fail_cuda(cudaError_t e, const char *what);
 // Lazily creates the context of `device` (stream, events, fixed buffers) and
 // makes it current.
 int ctx_get(int device, DeviceCtx **out);
+
+// permanent() of a problem with more than kMaxCols active columns, through the
+// lane-split batch walk (pqperm_api_laplace.cu); g_mu held by the caller.
+int perm_wide_locked(const double *A, int R, int C, const int32_t *rows, const int32_t *cols,
+                     double out[2]);
 
 // Grow-only device / pinned-host scratch of the batched Laplace path.
 int grow_dev(DeviceCtx *c, int slot, size_t bytes);

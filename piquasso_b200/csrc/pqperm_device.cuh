@@ -51,8 +51,16 @@ struct LapProblem {
     uint16_t rowmode[kMaxDigits + 1];  // gather mode: row of U of the pinned row / of digit d-1
 };
 
+// Column tables of a WIDE problem (more than kMaxCols active columns, S = 32):
+// kept out of LapProblem so that the sampler's descriptors stay small.
+struct LapWide {
+    uint8_t colmult[kLapMaxCols];
+    uint16_t colmode[kLapMaxCols];
+};
+
 struct LapParams {
     const LapProblem *prob;
+    const LapWide *wide; // [nprob] when the launch is a wide one, else nullptr
     const double2 *U;    // gather mode (sampler): ldu x ldu matrix every problem is a minor of
     int ldu;
     const double2 *A2;   // packed mode: per-problem matrices

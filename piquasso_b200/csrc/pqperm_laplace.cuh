@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
     }
     __syncthreads();
     const LapProblem &Q = P.prob[s_prob];
+    const uint8_t *colmult = P.wide ? P.wide[s_prob].colmult : Q.colmult;
+    const uint16_t *colmode = P.wide ? P.wide[s_prob].colmode : Q.colmode;
     const int D = Q.D, q = Q.q, W = Q.W;
     {
         const int nelem = (D + 1) * NCP;
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                 const int r = i / NCP, j = i - r * NCP;
                 double2 v = make_double2(r == 0 ? 1.0 : 0.0, 0.0);
                 if (j < Q.nc) {
-                    v = P.U[(size_t)Q.rowmode[r] * P.ldu + Q.colmode[j]];
+                    v = P.U[(size_t)Q.rowmode[r] * P.ldu + colmode[j]];
                     if (r > 0) {
                         v.x *= 2.0;
                         v.y *= 2.0;
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                     if (j < j1) {
                         double tr = sr[j], ti = si[j];
                         if (!UNITCOLS) {
-                            const int cm = Q.colmult[j * S + h];
+                            const int cm = colmult[j * S + h];
                             for (int k = 1; k < cm; k++)
                                 cmul(tr, ti, sr[j], si[j]);
                         }
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                     if (j < j1) {
                         double pr = prer[c], pi = prei[c];
                         if (!UNITCOLS) {
-                            const int cm = Q.colmult[j * S + h];
+                            const int cm = colmult[j * S + h];
                             for (int k = 1; k < cm; k++)
                                 cmul(pr, pi, sr[j], si[j]); // pre * s_j^{c_j - 1}
                         }
@@ -423,10 +425,12 @@ static __global__ void __launch_bounds__(128) sampler_pmf_kernel(const LapParams
                                                                  double *pmf)
 {
     const LapProblem &Q = P.prob[blockIdx.x];
-    __shared__ double2 w[kMaxCols];
+    const uint8_t *colmult = P.wide ? P.wide[blockIdx.x].colmult : Q.colmult;
+    const uint16_t *colmode = P.wide ? P.wide[blockIdx.x].colmode : Q.colmode;
+    __shared__ double2 w[kLapMaxCols];
     for (int k = threadIdx.x; k < Q.nc; k += 128) {
         const double2 v = P.out[(size_t)blockIdx.x * ncp1 + k];
-        const double c = (double)Q.colmult[k];
+        const double c = (double)colmult[k];
         w[k] = make_double2(c * v.x, c * v.y);
     }
     __syncthreads();
@@ -434,7 +438,7 @@ static __global__ void __launch_bounds__(128) sampler_pmf_kernel(const LapParams
         double ar = 0.0, ai = 0.0;
         const double2 *row = U + (size_t)m * d;
         for (int k = 0; k < Q.nc; k++) {
-            const double2 u = row[Q.colmode[k]];
+            const double2 u = row[colmode[k]];
             ar += u.x * w[k].x - u.y * w[k].y;
             ai += u.x * w[k].y + u.y * w[k].x;
         }

@@ -6,6 +6,7 @@
 namespace pqperm {
 
 constexpr int kMaxCols = 64;            // register-resident row sums per thread
+constexpr int kLapMaxCols = 256;        // lane-split walk: 32 lanes x 8 columns (wide problems)
 constexpr int kMaxDigits = 64;          // Gray digits (active rows after the split)
 constexpr int kMaxLowDigits = 24;       // digits walked inside one segment
 constexpr int kMaxMultiplicity = 254;   // radix r+1 is stored in a byte
@@ -34,7 +35,10 @@ inline LapVariant laplace_variant(int nc)
         return {1, nc < 1 ? 1 : nc};
     if (nc <= 26)
         return {2, (nc + 1) / 2};
-    return {4, (nc + 3) / 4};
+    if (nc <= kMaxCols)
+        return {4, (nc + 3) / 4};
+    // wide problems (few rows, many columns): a whole warp per Gray segment
+    return {32, (nc + 31) / 32};
 }
 
 } // namespace pqperm

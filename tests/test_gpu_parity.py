@@ -654,3 +654,89 @@ def test_single_process_sampler_sharded_over_devices(lib):
     devices = list(range(min(ndev, 4))) if ndev > 1 else [0, 0]
     assert generate_samples(inp, 31, u, seed, devices=devices) == want
     assert generate_samples(inp, 31, u, seed, devices=[0]) == want
+
+
+def test_problems_wider_than_64_columns():
+    """65-256 active columns (few rows): permanent, permanent_laplace and the batch
+    entries go through the warp-per-segment walk (S = 32 lanes x up to 8 columns).
+    Such problems have high row multiplicities and the Glynn sum cancels heavily;
+    rank-1 unit-modulus matrices (closed form n! prod u^r prod v) are the
+    well-conditioned ones, the bar elsewhere is the reference-style double walk
+    measured against the long-double arbiter."""
+    from piquasso_b200.sampling import permanent_batch, permanent_laplace_batch
+    rng = np.random.default_rng(65)
+
+    def bar(ref_err):
+        return max(1e-10, 20 * ref_err)
+
+    def rank1(rows, seed, scale=1.0):
+        from fractions import Fraction
+        gen = np.random.default_rng(seed)
+        rows = np.array(rows)
+        n = int(rows.sum())
+        u = np.exp(2j * np.pi * gen.random(len(rows)))
+        v = np.exp(2j * np.pi * gen.random(n))
+        mag = float(Fraction(math.factorial(n)) * Fraction(scale) ** n)
+        return scale * np.outer(u, v), rows, np.ones(n, int), mag * np.prod(u ** rows) * np.prod(v)
+
+    # closed forms; 75, 96, 97 and 130 columns = 3, 3, 4 and 5 columns per lane.  How
+    # hard the Glynn sum cancels depends on the phases u: the seeds below are ones
+    # where the reference-style double walk itself stays below 1e-10.
+    for rows, seed in (([40, 35], 10), ([30, 30, 36], 9), ([50, 47], 10), ([70, 60], 10),
+                       ([0, 33, 0, 40, 7], 0)):
+        a, rows, cols, exact = rank1(rows, seed)
+        assert relerr(oracle.permanent(a, rows, cols, precision=1), exact) < 1e-13, rows
+        ref_err = relerr(oracle.permanent(a, rows, cols), exact)
+        assert ref_err < 1e-10
+        assert relerr(complex(permanent(a, rows, cols)), exact) <= bar(ref_err), rows
+    # heavier cancellation (the double walk itself is at 5e-6): 65 columns, one row
+    a, rows, cols, _ = rank1([65], 1)
+    want = oracle.permanent(a, rows, cols, precision=1)
+    ref_err = relerr(oracle.permanent(a, rows, cols), want)
+    assert relerr(complex(permanent(a, rows, cols)), want) <= bar(ref_err)
+    # zero rows / columns in between and column multiplicities (unfiltered call):
+    # perm = n! prod u^r prod v^c for the rank-1 matrix
+    gen = np.random.default_rng(0)
+    rows = np.array([0, 33, 0, 40, 7])
+    cols = np.concatenate([np.ones(60, int), [0, 0], 2 * np.ones(10, int), [0]])
+    u = np.exp(2j * np.pi * gen.random(5))
+    v = np.exp(2j * np.pi * gen.random(len(cols)))
+    a = np.outer(u, v)
+    exact = float(math.factorial(80)) * np.prod(u ** rows) * np.prod(v ** cols)
+    ref_err = relerr(oracle.permanent(a, rows, cols), exact)
+    assert ref_err < 1e-10
+    assert relerr(complex(permanent(a, rows, cols)), exact) <= bar(ref_err)
+    with pytest.raises(RuntimeError):
+        permanent(a, rows + 1, cols)  # sum mismatch is still reported
+    # batch of wide permanents of one matrix (same closed form, other row vectors)
+    rb = np.array([[0, 33, 0, 40, 7], [7, 0, 40, 0, 33], [0, 40, 0, 40, 0]])
+    got = permanent_batch(a, rb, cols)
+    for b in range(len(rb)):
+        w = oracle.permanent(a, rb[b], cols, precision=1)
+        e = relerr(oracle.permanent(a, rb[b], cols), w)
+        assert relerr(complex(got[b]), w) <= bar(e), b
+    # permanent_laplace, 75 / 97 / 130 columns, single call and batch:
+    # out_l = (n-1)! prod u^r prod_{j != l} v_j
+    probs, exacts = [], []
+    for rows, nc in (([40, 34], 75), ([50, 46], 97), ([70, 59], 130)):
+        gen = np.random.default_rng(10)
+        rows = np.array(rows)
+        u = np.exp(2j * np.pi * gen.random(len(rows)))
+        v = np.exp(2j * np.pi * gen.random(nc))
+        probs.append((np.outer(u, v), rows, np.ones(nc, int)))
+        exacts.append(float(math.factorial(int(rows.sum()))) * np.prod(u ** rows) * np.prod(v) / v)
+    batch = permanent_laplace_batch(*zip(*probs))
+    for (a, rows, cols), exact, from_batch in zip(probs, exacts, batch):
+        ref_err = np.max(np.abs(oracle.permanent_laplace(a, rows, cols) - exact) / np.abs(exact))
+        assert ref_err < 1e-10
+        got = permanent_laplace(a, rows, cols)
+        assert got.shape == (len(cols),)
+        assert np.max(np.abs(got - exact) / np.abs(exact)) <= bar(ref_err), len(cols)
+        assert np.max(np.abs(from_batch - exact) / np.abs(exact)) <= bar(ref_err), len(cols)
+    # 256 columns: FP64 cannot resolve such a sum (the reference's own double walk is off
+    # by orders of magnitude); what can be checked is that the widest kernel runs and
+    # returns finite numbers, and that one column more is a clean error
+    a, rows, cols, _ = rank1([86, 85, 85], 2, 0.05)
+    assert np.isfinite(complex(permanent(a, rows, cols)))
+    with pytest.raises(ValueError):
+        permanent(np.ones((1, 257), complex), [257], np.ones(257, int))
