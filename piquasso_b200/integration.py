@@ -59,7 +59,7 @@ def make_adapters(pmf_rows=None, devices=None):
                                postselect_data, config):
         return sampling.generate_lossy_samples(
             input, shots, interferometer, config.seed_sequence,
-            postselect_data=postselect_data, pmf_rows=pmf_rows)
+            postselect_data=postselect_data, pmf_rows=pmf_rows, devices=devices)
 
     return generate_samples, generate_lossy_samples
 

@@ -278,7 +278,7 @@ def _generate_samples_by_coroutines(input, shots, interferometer, seed_sequence,
 
 
 def generate_lossy_samples(input, shots, interferometer, seed_sequence, postselect_data=None,
-                           pmf_rows=None):
+                           pmf_rows=None, devices=None):
     """Non-uniform losses (``generate_lossy_samples``, sampling.py:110-146 of the
     reference): sample the 2d-mode unitary dilation of the lossy transfer matrix
     and keep the first d modes."""
@@ -289,7 +289,7 @@ def generate_lossy_samples(input, shots, interferometer, seed_sequence, postsele
     expanded_input = np.concatenate([input, np.zeros_like(input)])
     samples = generate_samples(expanded_input, shots, expanded, seed_sequence,
                                reject_condition=None, postselect_data=postselect_data,
-                               pmf_rows=pmf_rows)
+                               pmf_rows=pmf_rows, devices=devices)
     return [s[: len(input)] for s in samples]
 
 
