@@ -231,7 +231,7 @@ static int launch_plan(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64_
         e = launch_binary(plan.NC, plan.B, P, reinterpret_cast<const double2 *>(c->d_A2),
                           c->num_sms, kMaxGrid, stream, &info);
     } else {
-        e = launch_generic(plan.NCP, fast, fast, P, c->num_sms, kMaxGrid, stream, &info);
+        e = launch_generic(plan.NCP, fast, plan.unitcols, P, c->num_sms, kMaxGrid, stream, &info);
     }
     if (e != cudaSuccess)
         return fail_cuda(e, plan.kernel == 2 ? "launch perm_walk_binary" : "launch perm_walk_generic");
@@ -366,13 +366,13 @@ static void fill_info(const Plan &plan, pq_plan_info *info)
     info->seg_len = plan.W;
     info->nseg = plan.nseg;
     info->active_rows = plan.D;
-    info->active_cols = plan.NC;
+    info->active_cols = plan.NC_active;
     info->low_digits = plan.q;
     info->kernel = plan.kernel;
     info->cols_padded = plan.NCP;
     info->sum_rows = plan.sum_rows;
     info->trivial = plan.trivial;
-    info->flops_per_term = 2.0 * plan.NC + 6.0 * plan.M + 2.0;
+    info->flops_per_term = 2.0 * plan.NC_active + 6.0 * plan.M + 2.0;
 }
 
 extern "C" int pq_perm_plan(int R, int C, const int32_t *rows, const int32_t *cols,

@@ -14,6 +14,9 @@ static cudaError_t launch_generic_nc(bool binary, bool unitcols, const WalkParam
     if (binary && unitcols)
         return launch_walk(perm_walk_generic<NC, true, true, NT>, P, P, NT, smem, num_sms,
                            max_grid, stream, info);
+    if (unitcols) // n-ary rows, unit (or expanded) columns: unrolled product chains
+        return launch_walk(perm_walk_generic<NC, false, true, NT>, P, P, NT, smem, num_sms,
+                           max_grid, stream, info);
     return launch_walk(perm_walk_generic<NC, false, false, NT>, P, P, NT, smem, num_sms,
                        max_grid, stream, info);
 }

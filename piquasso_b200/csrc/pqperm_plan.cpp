@@ -116,6 +116,23 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
         err = "more than 64 columns with non-zero multiplicity";
         return PQ_ERR_TOO_LARGE;
     }
+    plan.NC_active = plan.NC;
+    // A column of multiplicity c is written out as c unit columns while the
+    // expanded width still fits the registers: s_j^c becomes c factors of an
+    // unrolled product with independent chains instead of a run-time loop on one
+    // dependent chain, at the price of 2(c-1) more row-sum FMAs per term.  The
+    // terms -- hence the enumeration and the partition -- do not change.
+    if (!plan.unitcols && plan.M <= PQ_MAX_COLS) {
+        std::vector<int> src;
+        src.reserve((size_t)plan.M);
+        for (int j = 0; j < plan.NC; j++)
+            for (int k = 0; k < plan.colmult[j]; k++)
+                src.push_back(plan.src_col[j]);
+        plan.src_col.swap(src);
+        plan.colmult.assign((size_t)plan.M, 1);
+        plan.NC = plan.M;
+        plan.unitcols = true;
+    }
 
     // ---- kernel choice ------------------------------------------------------
     int choice = opt.kernel_choice;

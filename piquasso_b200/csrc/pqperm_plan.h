@@ -25,7 +25,8 @@ struct Plan {
 
     // compacted problem
     int D = 0;                // digits with radix >= 2
-    int NC = 0;               // columns with multiplicity > 0
+    int NC = 0;               // columns the kernels see (after the expansion below)
+    int NC_active = 0;        // columns of the caller's matrix with multiplicity > 0
     int NCP = 0;              // columns the chosen kernel is instantiated for
     int M = 0;                // sum of column multiplicities
     bool binary = false;      // every radix is 2
