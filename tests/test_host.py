@@ -343,3 +343,33 @@ def test_sampler_level_dropin_adapters():
     assert fake_sampling.generate_lossy_samples is stock_generate_samples
     with pytest.raises(ImportError):
         integration.install(modules=[SimpleNamespace()])
+
+
+def test_plan_expands_multiplicity_columns_without_touching_the_enumeration(lib):
+    """Columns of multiplicity c are handed to the kernels as c unit columns
+    (cols_padded covers sum(c)), the reported algorithmic figures and the
+    offset -> Gray-digit map stay those of the caller's problem."""
+    rows = np.array([2, 0, 1, 3, 1])
+    cols = np.array([3, 0, 2, 1, 1])
+    p = plan.plan(rows, cols)
+    assert p["active_cols"] == 4 and p["cols_padded"] == 8  # 7 unit columns, padded to 8
+    assert p["flops_per_term"] == 2 * 4 + 6 * 7 + 2
+    _, _, idx_max = oracle.gray_of_offset(rows, 0)
+    assert p["idx_max"] == idx_max
+    for off in range(0, idx_max, 5):
+        want, _, _ = oracle.gray_of_offset(rows, off)
+        assert list(plan.gray_of_offset(rows, off)) == list(want)
+    # too many photons to expand: the multiplicity columns stay as they are
+    wide = plan.plan(np.array([40, 40]), np.array([2] * 40))
+    assert wide["active_cols"] == 40 and wide["cols_padded"] == 40
+
+
+def test_sampler_batch_bounds():
+    from piquasso_b200.sampling import _batch_bounds
+    assert _batch_bounds(10, None, 1) == [(0, 10)]
+    assert _batch_bounds(0, None, 1) == []
+    assert _batch_bounds(10, 4, 1) == [(0, 4), (4, 8), (8, 10)]
+    assert _batch_bounds(500, None, 2) == [(0, 500)]  # too few shots to split
+    bounds = _batch_bounds(10000, None, 2)
+    assert bounds[0][0] == 0 and bounds[-1][1] == 10000 and len(bounds) == 4
+    assert all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
