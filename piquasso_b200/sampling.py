@@ -301,9 +301,9 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
     Restates ``_generate_samples`` / ``_generate_sample`` / ``_calculate_pmf``
     (``piquasso/_simulators/passive/sampling.py:149-236, 723-753``) with the
     loops interchanged: outer loop over the n photons, inner (batched) loop over
-    shots.  Per photon step ONE library call (``pq_sampler_pmf_c128``) filters
-    the zeros, walks all shots' Laplace problems on the GPU and assembles the
-    pmf rows on the device.
+    shots.  Per photon step ONE library call (``pq_sampler_draw_c128``) filters
+    the zeros, walks all shots' Laplace problems on the GPU, assembles the pmf
+    rows on the device and draws from them there.
 
     Host RNG order is the reference's: shot ``idx`` owns
     ``np.random.default_rng(seed_sequence + idx)`` and per photon draws
@@ -408,11 +408,6 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
             sample[live, index] += 1
         return [tuple(row) for row in sample.tolist()]
 
-    # Shots are independent, so batches may run concurrently: while one batch
-    # waits for the GPU inside the library call (GIL released, calls serialised
-    # by the library), another does its host bookkeeping.  Unequal batch sizes
-    # keep the two threads out of step -- one in its host-bound early photons
-    # while the other is in its GPU-bound late ones.
     if devices is not None and len(devices) > 1 and pmf_rows is None and shots >= len(devices):
         # one process, several GPUs: equal contiguous shot ranges, one host thread per
         # device (the library serialises per device, not globally); no exchange step
@@ -424,6 +419,11 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
             parts = list(pool.map(lambda job: run_batch(*job), jobs))
         return [smp for part in parts for smp in part]
     device = int(devices[0]) if devices is not None and len(devices) == 1 else None
+    # Shots are independent, so batches may also run concurrently on ONE device:
+    # while one batch waits for the GPU inside the library call (GIL released,
+    # device phases serialised by the library), another does its host bookkeeping
+    # and planning.  Unequal batch sizes keep the threads out of step -- one in
+    # its host-bound early photons while the other is in its GPU-bound late ones.
     bounds = _batch_bounds(shots, batch_shots, overlap if pmf_rows is None else 1)
     if len(bounds) <= 1 or overlap <= 1 or pmf_rows is not None:
         parts = [run_batch(b, e, device) for b, e in bounds]
