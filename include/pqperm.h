@@ -165,6 +165,13 @@ int pq_sampler_draw_dev_c128(int device, const double *U, int d, int nshots,
                              const int32_t *out_occ, const int32_t *in_occ, const double *u,
                              int32_t *index);
 
+/* Where the calling thread's last pq_sampler_* call spent its wall time, in
+ * milliseconds: out_ms[0] planning on the host (zero filtering, problem
+ * descriptors), [1] waiting for the device's lock, [2] the device phase (uploads,
+ * kernels, download, scatter), [3] the kernels alone (CUDA events).  Diagnostic
+ * only; the reference has no counterpart. */
+void pq_last_sampler_profile(double out_ms[4]);
+
 /* ---------------------------------------------------------------------
  * Partitioned permanent: the piece of one permanent that rank `part` of
  * `nparts` owns.  The term space [0, idx_max) (src/permanent.cpp:131-142) is

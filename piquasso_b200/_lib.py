@@ -71,6 +71,7 @@ SIGNATURES = [
      [c_double_p, ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, c_double_p]),
     ("pq_sampler_draw_c128", ctypes.c_int,
      [c_double_p, ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, c_double_p, c_int32_p]),
+    ("pq_last_sampler_profile", None, [c_double_p]),
     ("pq_sampler_draw_dev_c128", ctypes.c_int,
      [ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, c_double_p,
       c_int32_p]),

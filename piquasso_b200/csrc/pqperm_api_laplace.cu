@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -440,6 +441,11 @@ int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const
 }
 
 // One photon step of the sampler for nshots shots sharing one interferometer.
+// Host-side phases of the calling thread's last sampler step, in milliseconds:
+// planning, waiting for the device lock, device phase (uploads, kernels,
+// download, scatter), and the kernels alone (CUDA events).
+thread_local double g_sampler_profile[4] = {0.0, 0.0, 0.0, 0.0};
+
 // numpy's Generator.choice(d, p = row / sum(row)) for the uniform variate u, on
 // the host (shots whose Laplace problem is the reference's early-out)
 int draw_from_row(const double *row, int d, double u)
@@ -482,6 +488,12 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
             return rc0 ? rc0 : fail(PQ_ERR_NO_DEVICE, "no usable CUDA device");
         }
     }
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point a) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a)
+            .count();
+    };
+    g_sampler_profile[0] = g_sampler_profile[1] = g_sampler_profile[2] = g_sampler_profile[3] = 0.0;
     // Shots are planned independently: with thousands of them the range is cut
     // over a few host threads, each filling its own buckets, merged in shot order.
     struct Part {
@@ -596,6 +608,7 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
             }
         }
     }
+    g_sampler_profile[0] = ms_since(t_begin);
     if (!any) {
         // nothing to launch (e.g. the first photon of every shot): no kernel time
         std::lock_guard<std::mutex> lock(g_mu);
@@ -613,7 +626,10 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
         if ((rc = ctx_get(device >= 0 ? device : g_devices[0], &c)))
             return rc;
     }
+    const auto t_planned = std::chrono::steady_clock::now();
     std::lock_guard<std::mutex> dev_lock(c->mu);
+    g_sampler_profile[1] = ms_since(t_planned);
+    const auto t_locked = std::chrono::steady_clock::now();
     const size_t ubytes = (size_t)d * d * sizeof(double2);
     if ((rc = grow_dev(c, 4, ubytes)))
         return rc;
@@ -632,6 +648,8 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
         if (rc)
             return rc;
     }
+    g_sampler_profile[2] = ms_since(t_locked);
+    g_sampler_profile[3] = c->last_kernel_ms > 0.0 ? c->last_kernel_ms : 0.0;
     return PQ_OK;
 }
 
@@ -758,6 +776,12 @@ extern "C" int pq_sampler_draw_c128(const double *U, int d, int nshots, const in
     if (nshots == 0)
         return PQ_OK;
     return sampler_step(U, d, nshots, out_occ, in_occ, nullptr, u, index);
+}
+
+extern "C" void pq_last_sampler_profile(double out_ms[4])
+{
+    for (int i = 0; i < 4; i++)
+        out_ms[i] = g_sampler_profile[i];
 }
 
 extern "C" int pq_sampler_draw_dev_c128(int device, const double *U, int d, int nshots,

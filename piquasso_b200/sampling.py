@@ -13,6 +13,8 @@ same seed.
 
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 
 from . import _lib
@@ -231,9 +233,11 @@ def sampler_draw(interferometer, out_occ, in_occ, uniforms, device=None):
     _lib.check(rc)
     if (index < 0).any():
         raise ValueError("probabilities contain NaN")  # numpy's message for such a row
-    TIMERS["  of which GPU kernels (CUDA events)"] = (
-        TIMERS.get("  of which GPU kernels (CUDA events)", 0.0)
-        + max(lib.pq_last_kernel_ms(0 if device is None else int(device)), 0.0) * 1e-3)
+    prof = (ctypes.c_double * 4)()
+    lib.pq_last_sampler_profile(prof)
+    for name, ms in zip(("  of which planning (host threads)", "  of which waiting for the device",
+                         "  of which device phase", "  of which GPU kernels (CUDA events)"), prof):
+        TIMERS[name] = TIMERS.get(name, 0.0) + ms * 1e-3
     return index
 
 

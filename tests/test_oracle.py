@@ -136,6 +136,31 @@ def test_long_double_arbiter_and_closed_forms():
                       math.factorial(n)) < 1e-14
 
 
+def test_high_multiplicities_binomial_weights_beyond_2_to_63():
+    """With multiplicities of a few tens the weight prod C(r_i, g_i) exceeds 2^63
+    (C(40,20) * C(34,17) = 3e20): the oracle carries it as a long double, where the
+    reference's int overflows already above 2^31.  Closed forms: the rank-1 matrix
+    u v^T with multiplicities has perm = n! prod u^r prod v^c; permanent_laplace
+    entry l is (n-1)! prod u^r prod_{j != l} v_j."""
+    for rows, seed in (([40, 35], 10), ([50, 47], 10), ([0, 33, 0, 40, 7], 0)):
+        gen = np.random.default_rng(seed)
+        rows = np.array(rows)
+        n = int(rows.sum())
+        u = np.exp(2j * np.pi * gen.random(len(rows)))
+        v = np.exp(2j * np.pi * gen.random(n))
+        exact = float(math.factorial(n)) * np.prod(u ** rows) * np.prod(v)
+        a = np.outer(u, v)
+        assert relerr(oracle.permanent(a, rows, np.ones(n, int), precision=1), exact) < 1e-13
+        assert relerr(oracle.permanent(a, rows, np.ones(n, int)), exact) < 1e-10
+    gen = np.random.default_rng(10)
+    rows = np.array([40, 34])
+    u = np.exp(2j * np.pi * gen.random(2))
+    v = np.exp(2j * np.pi * gen.random(75))
+    exact = float(math.factorial(74)) * np.prod(u ** rows) * np.prod(v) / v
+    got = oracle.permanent_laplace(np.outer(u, v), rows, np.ones(75, int), precision=1)
+    assert np.max(np.abs(got - exact) / np.abs(exact)) < 1e-13
+
+
 def test_job_count_does_not_change_the_sum():
     """term(offset) is a pure function of the offset (src/permanent.cpp:158-164):
     any job split sums the same multiset of terms."""
