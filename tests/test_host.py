@@ -373,3 +373,25 @@ def test_sampler_batch_bounds():
     bounds = _batch_bounds(10000, None, 2)
     assert bounds[0][0] == 0 and bounds[-1][1] == 10000 and len(bounds) == 4
     assert all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+
+
+def test_sampler_edge_cases_on_the_host():
+    """Empty inputs, zero shots, everything rejected, every variant: shapes and
+    photon counts come out right (pmf rows from the oracle)."""
+    from conftest import haar, oracle_pmf_rows
+    from piquasso_b200.sampling import generate_lossy_samples, generate_samples
+    u = haar(4, 4)
+    kw = dict(pmf_rows=oracle_pmf_rows)
+    assert generate_samples([0, 0, 0, 0], 3, u, 1, **kw) == [(0, 0, 0, 0)] * 3
+    assert generate_samples([1, 0, 1, 0], 0, u, 1, **kw) == []
+    assert generate_samples([1, 0, 1, 0], 2, u, 1, reject_condition=lambda: True, **kw) == \
+        [(0, 0, 0, 0)] * 2
+    for smp in generate_samples([1, 0, 1, 0], 5, u, 1, uniform_particle_overlap=0.5, **kw):
+        assert len(smp) == 4 and sum(smp) == 2
+    assert generate_samples([0, 0, 0, 0], 2, u, 1, uniform_particle_overlap=0.5, **kw) == \
+        [(0, 0, 0, 0)] * 2
+    for smp in generate_samples([1, 0, 1, 0], 5, u, 1, postselect_data=((1,), (0,), 100), **kw):
+        assert len(smp) == 3 and sum(smp) == 2  # the post-selected mode is removed
+    for smp in generate_lossy_samples([1, 0, 1, 0], 5, 0.7 * u, 1, **kw):
+        assert len(smp) == 4 and sum(smp) <= 2
+    assert len(generate_samples([3, 0, 0, 0], 2, u, 1, devices=[0], **kw)) == 2
