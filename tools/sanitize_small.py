@@ -43,3 +43,20 @@ outs_ = np.array([rng.multinomial(k - 1, np.ones(7) / 7) if k > 1 else np.zeros(
 idx = sampler_draw(Ud, outs_, ins_, rng.random(2500))
 assert idx.min() >= 0 and idx.max() < 7
 print("sampler_draw ok")
+
+# wide problems (warp-per-segment walk, S = 32) and one large Laplace split over 3 parts
+from piquasso_b200.distributed import _laplace_device_partial
+gen = np.random.default_rng(10)
+rows_w = np.array([40, 35]); uw = np.exp(2j * np.pi * gen.random(2)); vw = np.exp(2j * np.pi * gen.random(75))
+import math
+exact = float(math.factorial(75)) * np.prod(uw ** rows_w) * np.prod(vw)
+got = complex(permanent(np.outer(uw, vw), rows_w, np.ones(75, int)))
+assert abs(got - exact) <= 1e-9 * abs(exact), ("wide", got, exact)
+aw = (rng.normal(size=(3, 70)) + 1j * rng.normal(size=(3, 70))) / 3
+lw = permanent_laplace(aw, [23, 23, 23], np.ones(70, int))
+assert lw.shape == (70,) and np.all(np.isfinite(lw))
+a16 = np.ascontiguousarray(unitary_group.rvs(18, random_state=3)[:15, :16])
+whole = permanent_laplace(a16, np.ones(15, int), np.ones(16, int))
+parts = sum(_laplace_device_partial(a16, np.ones(15, np.int32), np.ones(16, np.int32), g, 3) for g in range(3))
+assert np.allclose(parts, whole, rtol=1e-12)
+print("wide + laplace split ok")
