@@ -271,6 +271,17 @@ int pq_kernel_ms_history(int device, double *out, int max);
 /* Number of kernels the library has launched on all devices since load. */
 int64_t pq_launch_count(void);
 
+/* ACCURACY ARBITER (tests, accuracy reports -- not a fast path): the permanent
+ * of pq_perm_c128's arguments with every operation in double-double arithmetic
+ * (~106-bit mantissa) on the library's first device, returned as
+ * out = {re_hi, re_lo, im_hi, im_lo} (value = hi + lo).  Its Gray-code counter
+ * restates the reference's class literally (src/n_aryGrayCodeCounter.hpp:170-254)
+ * with 64-bit offsets and shares no device code with the production walks; it
+ * is what arbitrates Haar-random matrices beyond n = 32, where the reference
+ * itself is wrong (:179).  ~100x slower than pq_perm_c128.  At most 64 columns. */
+int pq_perm_arbiter_c128(const double *A, int R, int C, const int32_t *rows,
+                         const int32_t *cols, double out[4]);
+
 /* Measured FP64 peak of `device`: a dependent-free DFMA loop over all SMs,
  * `iters` FMAs per thread; returns TFLOP/s (2 flop per FMA), <0 on error. */
 double pq_fp64_peak_tflops(int device, int iters);

@@ -44,6 +44,10 @@ def _load_oracle():
         lib.pqo_permanent_c128.argtypes = [
             _c_double_p, ctypes.c_int, ctypes.c_int, _c_int_p, _c_int_p,
             ctypes.c_int, ctypes.c_int, _c_double_p]
+        lib.pqo_permanent_c128_hilo.restype = ctypes.c_int
+        lib.pqo_permanent_c128_hilo.argtypes = [
+            _c_double_p, ctypes.c_int, ctypes.c_int, _c_int_p, _c_int_p,
+            ctypes.c_int, ctypes.c_int, _c_double_p]
         lib.pqo_permanent_laplace_c128.restype = ctypes.c_int
         lib.pqo_permanent_laplace_c128.argtypes = [
             _c_double_p, ctypes.c_int, ctypes.c_int, _c_int_p, _c_int_p,
@@ -131,6 +135,22 @@ def permanent(matrix, rows, cols, njobs: int = 32, precision: int = 0) -> comple
     if rc:
         raise ValueError("bad arguments")
     return complex(out[0], out[1])
+
+
+def permanent_hilo(matrix, rows, cols, njobs: int = 32, precision: int = 2):
+    """The permanent in extended precision as a (hi, lo) pair of complex128
+    (value = hi + lo): ``precision=1`` long double, ``precision=2`` software
+    binary128 (``__float128``, ~50x slower than double -- fixtures only)."""
+    a, r, c = _prep(matrix, rows, cols)
+    out = np.zeros(4)
+    rc = _load_oracle().pqo_permanent_c128_hilo(
+        a.ctypes.data_as(_c_double_p), a.shape[0], a.shape[1], _ip(r), _ip(c),
+        njobs, precision, out.ctypes.data_as(_c_double_p))
+    if rc == 1:
+        raise RuntimeError("Number of input and output states should be equal")
+    if rc:
+        raise ValueError("bad arguments")
+    return complex(out[0], out[2]), complex(out[1], out[3])
 
 
 def permanent_laplace(matrix, rows, cols, njobs: int = 32, precision: int = 0):

@@ -99,6 +99,8 @@ SIGNATURES = [
       ctypes.c_int64, c_double_p]),
     ("pq_last_kernel_ms", ctypes.c_double, [ctypes.c_int]),
     ("pq_launch_count", ctypes.c_int64, []),
+    ("pq_perm_arbiter_c128", ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_int32_p,
+                                            c_int32_p, c_double_p]),
     ("pq_fp64_peak_tflops", ctypes.c_double, [ctypes.c_int, ctypes.c_int]),
     ("pq_set_kernel_choice", ctypes.c_int, [ctypes.c_int]),
     ("pq_set_seg_len_hint", ctypes.c_int, [ctypes.c_int64]),

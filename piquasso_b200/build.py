@@ -43,6 +43,8 @@ def _units():
         ("api_laplace", "pqperm_api_laplace.cu", []),
         ("plan", "pqperm_plan.cpp", []),
         ("generic", "pqperm_kernels_generic.cu", []),
+        # every FMA of the double-double arithmetic is explicit: no contraction
+        ("arbiter", "pqperm_arbiter.cu", ["-fmad=false"]),
         ("laplace_unit", "pqperm_kernels_laplace.cu", ["-DPQ_LAP_UNIT=1"]),
         ("laplace_general", "pqperm_kernels_laplace.cu", ["-DPQ_LAP_UNIT=0"]),
     ]

@@ -23,24 +23,25 @@ namespace pqperm {
 
 // parts of the binary kernel family (pqperm_kernels_binary.cu)
 #define PQ_DECL_PART(k)                                                                 \
-    cudaError_t launch_binary_part_##k(int, int, const WalkParams &, const double2 *, int,  \
-                                       int, cudaStream_t, LaunchInfo *);
+    cudaError_t launch_binary_part_##k(int, int, const WalkParams &, const double *,        \
+                                       const double2 *, int, int, cudaStream_t, LaunchInfo *);
 PQ_DECL_PART(0)
 PQ_DECL_PART(1)
 PQ_DECL_PART(2)
 PQ_DECL_PART(3)
 #undef PQ_DECL_PART
 
-cudaError_t launch_binary(int nc, int B, const WalkParams &P, const double2 *d_A2,
-                          int num_sms, int max_grid, cudaStream_t stream, LaunchInfo *info)
+cudaError_t launch_binary(int nc, int B, const WalkParams &P, const double *h_A2,
+                          const double2 *d_A2, int num_sms, int max_grid, cudaStream_t stream,
+                          LaunchInfo *info)
 {
     if (nc <= 20)
-        return launch_binary_part_0(nc, B, P, d_A2, num_sms, max_grid, stream, info);
+        return launch_binary_part_0(nc, B, P, h_A2, d_A2, num_sms, max_grid, stream, info);
     if (nc <= 30)
-        return launch_binary_part_1(nc, B, P, d_A2, num_sms, max_grid, stream, info);
+        return launch_binary_part_1(nc, B, P, h_A2, d_A2, num_sms, max_grid, stream, info);
     if (nc <= 40)
-        return launch_binary_part_2(nc, B, P, d_A2, num_sms, max_grid, stream, info);
-    return launch_binary_part_3(nc, B, P, d_A2, num_sms, max_grid, stream, info);
+        return launch_binary_part_2(nc, B, P, h_A2, d_A2, num_sms, max_grid, stream, info);
+    return launch_binary_part_3(nc, B, P, h_A2, d_A2, num_sms, max_grid, stream, info);
 }
 
 } // namespace pqperm
@@ -116,14 +117,20 @@ int ctx_get(int device, DeviceCtx **out)
             PQ_CUDA(cudaEventCreate(&c->ring0[i]));
             PQ_CUDA(cudaEventCreate(&c->ring1[i]));
         }
-        PQ_CUDA(cudaMalloc(&c->d_A2, kA2Doubles * sizeof(double)));
+        PQ_CUDA(cudaEventCreateWithFlags(&c->ev_busy, cudaEventDisableTiming));
+        PQ_CUDA(cudaMalloc(&c->d_blob, kBlobBytes));
+        PQ_CUDA(cudaMallocHost(&c->h_blob, kBlobBytes));
         PQ_CUDA(cudaMalloc(&c->d_partials, (size_t)kMaxGrid * 4 * sizeof(double)));
-        PQ_CUDA(cudaMalloc(&c->d_out, 4 * sizeof(double)));
-        PQ_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned long long)));
-        PQ_CUDA(cudaMalloc(&c->d_sched, (size_t)kMaxSegLenNary));
-        PQ_CUDA(cudaMalloc(&c->d_wtab, (size_t)kMaxSegLenNary * sizeof(double)));
-        PQ_CUDA(cudaMalloc(&c->d_binom, (size_t)kMaxDigits * 256 * sizeof(double)));
-        PQ_CUDA(cudaMallocHost(&c->h_pinned, (kA2Doubles + 8) * sizeof(double)));
+        PQ_CUDA(cudaHostAlloc(&c->h_out, 4 * sizeof(double), cudaHostAllocMapped));
+        PQ_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&c->d_hout), c->h_out, 0));
+        {
+            // dispenser and finished-CTA count: zero once, the kernels re-arm them
+            unsigned char *cnt = nullptr;
+            PQ_CUDA(cudaMalloc(&cnt, 16));
+            PQ_CUDA(cudaMemset(cnt, 0, 16));
+            c->d_counter = reinterpret_cast<unsigned long long *>(cnt);
+            c->d_done = reinterpret_cast<unsigned int *>(cnt + 8);
+        }
         c->ready = true;
     }
     *out = c;
@@ -158,16 +165,39 @@ int grow_host(DeviceCtx *c, int slot, size_t bytes)
     return PQ_OK;
 }
 
+// Layout of a plan's inputs inside the blob (device and pinned staging alike):
+// the matrix, then the binomial tables of the n-ary flavours.
+struct BlobLayout {
+    size_t a2 = 0, binom = 0, total = 0;
+    bool tables = false;
+};
+
+static BlobLayout blob_layout(const Plan &plan)
+{
+    BlobLayout L;
+    L.tables = !(plan.binary && plan.unitcols); // the binary fast paths need no tables
+    L.a2 = 0;
+    L.binom = plan.A2.size() * sizeof(double);
+    L.total = L.binom + (L.tables ? plan.binom.size() * sizeof(double) : 0);
+    return L;
+}
+
+// the binary walk whose matrix rides in the kernel parameters needs no upload at all
+static bool rides_in_params(const Plan &plan)
+{
+    return plan.kernel == 2 && plan.NC <= kBinMaxParamCols && plan.D + 1 == plan.NC;
+}
+
 static void fill_params(const Plan &plan, DeviceCtx *c, WalkParams &P)
 {
+    const BlobLayout L = blob_layout(plan);
     std::memset(&P, 0, sizeof(P));
-    P.A2 = reinterpret_cast<const double2 *>(c->d_A2);
-    P.sched = c->d_sched;
-    P.wtab = c->d_wtab;
-    P.binom = c->d_binom;
+    P.A2 = reinterpret_cast<const double2 *>(c->d_blob + L.a2);
+    P.binom = reinterpret_cast<const double *>(c->d_blob + L.binom);
     P.partials = c->d_partials;
     P.segsums = nullptr;
     P.counter = c->d_counter;
+    P.done = c->d_done;
     P.W = plan.W;
     P.D = plan.D;
     P.q = plan.q;
@@ -180,68 +210,89 @@ static void fill_params(const Plan &plan, DeviceCtx *c, WalkParams &P)
         P.colmult[j] = (uint8_t)plan.colmult[j];
 }
 
-// Enqueue upload + walk + reduction of segments [seg_begin, seg_end) on c's
-// stream; the four-double partial lands in d_dst (device) on that stream.
-// Stage the plan's matrix and tables into c's device buffers on `stream`.
+// Before `stream` touches the device's shared scratch: wait (on the device) for
+// the last launch if that ran on another stream.
+static int scratch_acquire(DeviceCtx *c, cudaStream_t stream)
+{
+    if (c->busy_valid && c->busy_stream != stream)
+        PQ_CUDA(cudaStreamWaitEvent(stream, c->ev_busy, 0));
+    return PQ_OK;
+}
+
+static int scratch_release(DeviceCtx *c, cudaStream_t stream)
+{
+    if (stream != c->stream) { // the library's own stream is always synchronised by its caller
+        PQ_CUDA(cudaEventRecord(c->ev_busy, stream));
+        c->busy_stream = stream;
+        c->busy_valid = true;
+    } else {
+        c->busy_valid = false;
+    }
+    return PQ_OK;
+}
+
+// Stage the plan's matrix and tables into c's blob on `stream`: ONE copy.
 static int upload_plan(const Plan &plan, DeviceCtx *c, cudaStream_t stream)
 {
+    if (rides_in_params(plan))
+        return PQ_OK; // the blob (and whichever job is resident in it) stays untouched
+    c->resident_job = 0;
+    int rc = scratch_acquire(c, stream);
+    if (rc)
+        return rc;
     // the pinned staging buffer may still feed the previous (caller-stream) upload
     if (c->up_pending) {
         PQ_CUDA(cudaEventSynchronize(c->ev_up));
         c->up_pending = false;
     }
-    c->resident_job = 0;
-    const size_t a2_bytes = plan.A2.size() * sizeof(double);
-    std::memcpy(c->h_pinned, plan.A2.data(), a2_bytes);
-    PQ_CUDA(cudaMemcpyAsync(c->d_A2, c->h_pinned, a2_bytes, cudaMemcpyHostToDevice, stream));
-    const bool fast = plan.binary && plan.unitcols; // tables are needed otherwise
-    if (!fast && plan.W > 1) {
-        PQ_CUDA(cudaMemcpyAsync(c->d_sched, plan.sched.data(), (size_t)plan.W,
-                                cudaMemcpyHostToDevice, stream));
-        PQ_CUDA(cudaMemcpyAsync(c->d_wtab, plan.wtab.data(), (size_t)plan.W * sizeof(double),
-                                cudaMemcpyHostToDevice, stream));
+    const BlobLayout L = blob_layout(plan);
+    if (L.total > kBlobBytes)
+        return fail(PQ_ERR_TOO_LARGE, "plan does not fit the staging blob");
+    std::memcpy(c->h_blob + L.a2, plan.A2.data(), plan.A2.size() * sizeof(double));
+    if (L.tables && !plan.binom.empty())
+        std::memcpy(c->h_blob + L.binom, plan.binom.data(), plan.binom.size() * sizeof(double));
+    PQ_CUDA(cudaMemcpyAsync(c->d_blob, c->h_blob, L.total, cudaMemcpyHostToDevice, stream));
+    if (stream != c->stream) {
+        PQ_CUDA(cudaEventRecord(c->ev_up, stream));
+        c->up_pending = true;
     }
-    if (!fast && !plan.binom.empty())
-        PQ_CUDA(cudaMemcpyAsync(c->d_binom, plan.binom.data(),
-                                plan.binom.size() * sizeof(double), cudaMemcpyHostToDevice,
-                                stream));
-    PQ_CUDA(cudaEventRecord(c->ev_up, stream));
-    c->up_pending = true;
     return PQ_OK;
 }
 
-// Enqueue walk + reduction of segments [seg_begin, seg_end) on `stream`, inputs
-// already resident (upload_plan); the four-double partial lands in d_dst.  The
-// kernels are bracketed by an event pair of the timing ring.
+// Enqueue the walk of segments [seg_begin, seg_end) on `stream`, inputs already
+// resident (upload_plan) or riding in the kernel parameters; the four-double sum
+// lands in d_dst (device or mapped host memory), written by the kernel's last CTA.
+// ONE launch, bracketed by an event pair of the timing ring.
 static int launch_plan(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64_t seg_end,
                        double *d_dst, double *d_segsums, cudaStream_t stream)
 {
+    int rc = scratch_acquire(c, stream);
+    if (rc)
+        return rc;
     WalkParams P;
     fill_params(plan, c, P);
     P.seg_begin = seg_begin;
     P.seg_end = seg_end;
     P.segsums = d_segsums;
+    P.out4 = d_dst;
     LaunchInfo info;
     cudaError_t e;
     const bool fast = plan.binary && plan.unitcols;
-    PQ_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), stream));
     const int slot = (int)(c->ring_next % kTimingRing);
     PQ_CUDA(cudaEventRecord(c->ring0[slot], stream));
     if (plan.kernel == 2) {
-        e = launch_binary(plan.NC, plan.B, P, reinterpret_cast<const double2 *>(c->d_A2),
-                          c->num_sms, kMaxGrid, stream, &info);
+        e = launch_binary(plan.NC, plan.B, P, rides_in_params(plan) ? plan.A2.data() : nullptr,
+                          reinterpret_cast<const double2 *>(c->d_blob), c->num_sms, kMaxGrid,
+                          stream, &info);
     } else {
         e = launch_generic(plan.NCP, fast, plan.unitcols, P, c->num_sms, kMaxGrid, stream, &info);
     }
     if (e != cudaSuccess)
         return fail_cuda(e, plan.kernel == 2 ? "launch perm_walk_binary" : "launch perm_walk_generic");
-    e = launch_reduce_partials(c->d_partials, info.grid, d_dst, stream);
-    if (e != cudaSuccess)
-        return fail_cuda(e, "launch reduce_partials");
     PQ_CUDA(cudaEventRecord(c->ring1[slot], stream));
     c->ring_next++;
-    g_launches += 2;
-    return PQ_OK;
+    g_launches += 1;
+    return scratch_release(c, stream);
 }
 
 static int enqueue_walk(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64_t seg_end,
@@ -251,6 +302,19 @@ static int enqueue_walk(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64
     if (rc)
         return rc;
     return launch_plan(plan, c, seg_begin, seg_end, d_dst, d_segsums, stream);
+}
+
+// duration of the most recent launch_plan on c (its stream must be synchronised)
+static void note_last_kernel_ms(DeviceCtx *c)
+{
+    if (c->ring_next == 0)
+        return;
+    const int slot = (int)((c->ring_next - 1) % kTimingRing);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ring0[slot], c->ring1[slot]) == cudaSuccess)
+        c->last_kernel_ms = ms;
+    else
+        cudaGetLastError();
 }
 
 static PlanOptions plan_options(int num_sms)
@@ -442,7 +506,7 @@ static int perm_run(const double *A, int R, int C, const int32_t *rows, const in
     std::string err;
     {
         PlanOptions o = plan_options(148);
-        const int rc = make_plan(nullptr, R, C, rows, cols, o, plan, err);
+        const int rc = make_plan(A, R, C, rows, cols, o, plan, err);
         if (rc)
             return fail(rc, err);
         if (plan.trivial) {
@@ -459,8 +523,10 @@ static int perm_run(const double *A, int R, int C, const int32_t *rows, const in
         if (rc)
             return rc;
     }
-    {
-        PlanOptions o = plan_options(ctx[0]->num_sms * ndev);
+    if (ctx[0]->num_sms != 148) {
+        // the partition is planned for ONE device's SM count whatever the number of
+        // devices or ranks, so that every split of a problem cuts the same segments
+        PlanOptions o = plan_options(ctx[0]->num_sms);
         const int rc = make_plan(A, R, C, rows, cols, o, plan, err);
         if (rc)
             return fail(rc, err);
@@ -469,27 +535,24 @@ static int perm_run(const double *A, int R, int C, const int32_t *rows, const in
     const int used = (ndev > 1 && plan.nseg >= (int64_t)ndev * 4096) ? std::min(ndev, 64) : 1;
     for (int i = 0; i < used; i++) {
         DeviceCtx *c = ctx[i];
-        PQ_CUDA(cudaSetDevice(c->device));
+        if (ndev > 1)
+            PQ_CUDA(cudaSetDevice(c->device));
         int64_t b, e;
         split_range(plan.nseg, i, used, &b, &e);
-        PQ_CUDA(cudaEventRecord(c->ev0, c->stream));
-        const int rc = enqueue_walk(plan, c, b, e, c->d_out, nullptr, c->stream);
+        // the kernel's last CTA writes the sum straight into mapped host memory
+        const int rc = enqueue_walk(plan, c, b, e, c->d_hout, nullptr, c->stream);
         if (rc)
             return rc;
-        PQ_CUDA(cudaEventRecord(c->ev1, c->stream));
-        PQ_CUDA(cudaMemcpyAsync(c->h_pinned + kA2Doubles, c->d_out, 4 * sizeof(double),
-                                cudaMemcpyDeviceToHost, c->stream));
     }
     double quads[4 * 64];
     for (int i = 0; i < used; i++) {
         DeviceCtx *c = ctx[i];
-        PQ_CUDA(cudaSetDevice(c->device));
+        if (ndev > 1)
+            PQ_CUDA(cudaSetDevice(c->device));
         PQ_CUDA(cudaStreamSynchronize(c->stream));
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
-            c->last_kernel_ms = ms;
+        note_last_kernel_ms(c);
         for (int k = 0; k < 4; k++)
-            quads[4 * i + k] = c->h_pinned[kA2Doubles + k];
+            quads[4 * i + k] = c->h_out[k];
     }
     double tot[4];
     pq_perm_combine(quads, used, tot); // fixed device order, error-free
@@ -531,7 +594,7 @@ extern "C" int pq_perm_partial_c128(const double *A, int R, int C, const int32_t
     std::string err;
     {
         PlanOptions o = plan_options(148);
-        const int rc = make_plan(nullptr, R, C, rows, cols, o, plan, err);
+        const int rc = make_plan(A, R, C, rows, cols, o, plan, err);
         if (rc)
             return fail(rc, err);
         if (plan.trivial) {
@@ -548,9 +611,10 @@ extern "C" int pq_perm_partial_c128(const double *A, int R, int C, const int32_t
     int rc = ctx_get(device, &c);
     if (rc)
         return rc;
-    {
-        // plan for the whole job so that every rank cuts the term space identically
-        PlanOptions o = plan_options(c->num_sms * nparts);
+    if (c->num_sms != 148) {
+        // planned for ONE device's SM count whatever nparts is: every rank, and every
+        // rank count, cuts the term space into the same segments
+        PlanOptions o = plan_options(c->num_sms);
         rc = make_plan(A, R, C, rows, cols, o, plan, err);
         if (rc)
             return fail(rc, err);
@@ -558,7 +622,6 @@ extern "C" int pq_perm_partial_c128(const double *A, int R, int C, const int32_t
     int64_t b, e;
     split_range(plan.nseg, part, nparts, &b, &e);
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
-    PQ_CUDA(cudaEventRecord(c->ev0, s));
     if (b < e) {
         rc = enqueue_walk(plan, c, b, e, d_partial, nullptr, s);
         if (rc)
@@ -566,12 +629,10 @@ extern "C" int pq_perm_partial_c128(const double *A, int R, int C, const int32_t
     } else {
         PQ_CUDA(cudaMemsetAsync(d_partial, 0, 4 * sizeof(double), s));
     }
-    PQ_CUDA(cudaEventRecord(c->ev1, s));
     if (!stream) {
         PQ_CUDA(cudaStreamSynchronize(s));
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
-            c->last_kernel_ms = ms;
+        if (b < e)
+            note_last_kernel_ms(c);
     }
     if (status)
         *status = 0;
@@ -602,7 +663,7 @@ extern "C" int pq_perm_segment_sums_c128(const double *A, int R, int C, const in
     double *d_seg = nullptr;
     PQ_CUDA(cudaMalloc(&d_seg, (size_t)nseg * 2 * sizeof(double)));
     PQ_CUDA(cudaMemsetAsync(d_seg, 0, (size_t)nseg * 2 * sizeof(double), c->stream));
-    rc = enqueue_walk(plan, c, seg_begin, seg_begin + nseg, c->d_out, d_seg, c->stream);
+    rc = enqueue_walk(plan, c, seg_begin, seg_begin + nseg, c->d_hout, d_seg, c->stream);
     if (rc == PQ_OK) {
         cudaError_t e = cudaMemcpyAsync(out, d_seg, (size_t)nseg * 2 * sizeof(double),
                                         cudaMemcpyDeviceToHost, c->stream);
@@ -628,7 +689,7 @@ extern "C" double pq_fp64_peak_tflops(int device, int iters)
         double flops = 0.0;
         if (cudaEventRecord(c->ev0, c->stream) != cudaSuccess)
             return -1.0;
-        if (launch_dfma_probe(c->num_sms, iters, c->d_out, c->stream, &flops) != cudaSuccess)
+        if (launch_dfma_probe(c->num_sms, iters, c->d_partials, c->stream, &flops) != cudaSuccess)
             return -1.0;
         g_launches += 1;
         cudaEventRecord(c->ev1, c->stream);
@@ -665,7 +726,7 @@ extern "C" int pq_perm_job_create_c128(const double *A, int R, int C, const int3
     std::string err;
     {
         PlanOptions o = plan_options(148);
-        const int rc = make_plan(nullptr, R, C, rows, cols, o, j->plan, err);
+        const int rc = make_plan(A, R, C, rows, cols, o, j->plan, err);
         if (rc)
             return fail(rc, err);
         if (j->plan.trivial) {
@@ -682,18 +743,22 @@ extern "C" int pq_perm_job_create_c128(const double *A, int R, int C, const int3
     int rc = ctx_get(device, &c);
     if (rc)
         return rc;
-    PlanOptions o = plan_options(c->num_sms * nparts);
-    rc = make_plan(A, R, C, rows, cols, o, j->plan, err);
-    if (rc)
-        return fail(rc, err);
+    if (c->num_sms != 148) {
+        PlanOptions o = plan_options(c->num_sms); // one device's SM count: same cut at every nparts
+        rc = make_plan(A, R, C, rows, cols, o, j->plan, err);
+        if (rc)
+            return fail(rc, err);
+    }
     j->id = g_job_ids++;
     j->device = device;
     split_range(j->plan.nseg, part, nparts, &j->seg_begin, &j->seg_end);
-    rc = upload_plan(j->plan, c, c->stream);
-    if (rc)
-        return rc;
-    PQ_CUDA(cudaStreamSynchronize(c->stream));
-    c->resident_job = j->id;
+    if (!rides_in_params(j->plan)) {
+        rc = upload_plan(j->plan, c, c->stream);
+        if (rc)
+            return rc;
+        PQ_CUDA(cudaStreamSynchronize(c->stream));
+        c->resident_job = j->id;
+    }
     if (status)
         *status = 0;
     *job = j.release();
@@ -710,7 +775,8 @@ extern "C" int pq_perm_job_launch(pq_perm_job *job, void *stream, double *d_part
     if (rc)
         return rc;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
-    if (c->resident_job != job->id) { // evicted by another call on this device
+    if (!rides_in_params(job->plan) && c->resident_job != job->id) {
+        // evicted by another call on this device
         rc = upload_plan(job->plan, c, s);
         if (rc)
             return rc;

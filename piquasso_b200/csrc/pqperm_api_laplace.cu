@@ -158,13 +158,11 @@ void lap_fill(const LapShape &sh, int ncp, LapProblem &q, LapWide *wide = nullpt
     }
 }
 
-// Shared memory of one CTA of the walk for this shape, and the limit it must fit
-// (the (D+1) x NCP matrix is staged per CTA; wide problems with many rows do not).
-constexpr size_t kLapSmemLimit = 200 * 1024;
+// The (D+1) x NCP matrix is staged per CTA beside the threads' double-double
+// totals (lap_smem_bytes, pqperm_limits.h); wide problems with many rows do not fit.
 const char *const kLapTooWide =
     "problem too large for the lane-split walk: (active rows + 1) x padded columns x 16 bytes "
-    "exceeds 200 KB of shared memory";
-inline size_t lap_smem_bytes(int D, int ncp) { return (size_t)(D + 1) * ncp * sizeof(double2); }
+    "plus the accumulators exceeds 224 KB of shared memory";
 
 struct Bucket {
     int S = 0, NCL = 0;
@@ -231,7 +229,7 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
     const size_t out_bytes = (size_t)n * ncp1 * sizeof(double2);
     int rc;
     if ((rc = grow_dev(c, 0, sizeof(LapProblem) * (size_t)n)) ||
-        (rc = grow_dev(c, 2, (size_t)total_blocks * ncp1 * sizeof(double2))) ||
+        (rc = grow_dev(c, 2, (size_t)total_blocks * ncp1 * 4 * sizeof(double))) ||
         (rc = grow_dev(c, 3, out_bytes)))
         return rc;
     cudaStream_t st = c->stream;
@@ -263,11 +261,12 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
         PQ_CUDA(cudaMemcpyAsync(c->d_lap[8], bk.wide.data(), wbytes, cudaMemcpyHostToDevice, st));
         P.wide = reinterpret_cast<const LapWide *>(c->d_lap[8]);
     }
-    P.partials = reinterpret_cast<double2 *>(c->d_lap[2]);
+    P.partials = reinterpret_cast<double *>(c->d_lap[2]);
     P.out = reinterpret_cast<double2 *>(c->d_lap[3]);
     P.nprob = n;
     P.perm_only = (epi && epi->perm_only) ? 1 : 0;
-    const size_t smem = (size_t)(bk.max_D + 1) * NCP * sizeof(double2);
+    P.max_D = bk.max_D;
+    const size_t smem = lap_smem_bytes(bk.max_D, bk.S, bk.NCL);
     PQ_CUDA(cudaEventRecord(c->lap_ev0, st));
     cudaError_t e = launch_laplace(bk.S, bk.NCL, bk.unit, P, total_blocks, smem, st);
     if (e != cudaSuccess)
@@ -367,7 +366,7 @@ int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const
         const LapVariant v = laplace_variant(sh.NC);
         Bucket &bk = g_buckets.get(v, sh.unit);
         const int NCP = v.S * v.NCL;
-        if (lap_smem_bytes(sh.D, NCP) > kLapSmemLimit)
+        if (lap_smem_bytes(sh.D, v.S, v.NCL) > kLapSmemLimit)
             return fail(PQ_ERR_TOO_LARGE, kLapTooWide);
         LapProblem q;
         LapWide w;
@@ -537,7 +536,7 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
             }
             const LapVariant v = laplace_variant(sh.NC);
             Bucket &bk = buckets.get(v, sh.unit);
-            if (lap_smem_bytes(sh.D, v.S * v.NCL) > kLapSmemLimit) {
+            if (lap_smem_bytes(sh.D, v.S, v.NCL) > kLapSmemLimit) {
                 part.rc = PQ_ERR_TOO_LARGE;
                 part.err = kLapTooWide;
                 return;
@@ -684,7 +683,7 @@ int perm_batch_locked(const double *U, int R, int C, int nprob, const int32_t *r
         }
         const LapVariant v = laplace_variant(sh.NC);
         Bucket &bk = g_buckets.get(v, sh.unit);
-        if (lap_smem_bytes(sh.D, v.S * v.NCL) > kLapSmemLimit)
+        if (lap_smem_bytes(sh.D, v.S, v.NCL) > kLapSmemLimit)
             return fail(PQ_ERR_TOO_LARGE, kLapTooWide);
         LapProblem q;
         LapWide w;

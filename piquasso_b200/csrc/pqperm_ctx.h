@@ -20,24 +20,35 @@ constexpr int kMaxGrid = 148 * 32 * 2;
 constexpr int kTimingRing = 64;
 constexpr size_t kA2Doubles = (size_t)(kMaxDigits + 1) * kMaxCols * 2;
 
+// Staging blob of one permanent: [A2 | binomial tables], one H2D copy.
+constexpr size_t kBlobBytes =
+    kA2Doubles * sizeof(double) + (size_t)kMaxDigits * 256 * sizeof(double);
+
 struct DeviceCtx {
     int device = -1;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t ev_up = nullptr;   // uploads of the last enqueue have left h_pinned
+    cudaEvent_t ev_up = nullptr;   // the last upload has left h_blob
     bool up_pending = false;
-    double *d_A2 = nullptr;        // (kMaxDigits+1) x kMaxCols double2
+    // The walk kernels of one device share the scratch below (blob, partials,
+    // counters, the __constant__ matrix).  A launch on a caller's stream may still
+    // be running when the next call arrives on another stream: ev_busy is recorded
+    // behind every launch and waited for (on the device, cudaStreamWaitEvent) by
+    // the next upload / launch that uses a different stream.
+    cudaEvent_t ev_busy = nullptr;
+    cudaStream_t busy_stream = nullptr;
+    bool busy_valid = false;
+    unsigned char *d_blob = nullptr;   // kBlobBytes: matrix and tables of the resident plan
+    unsigned char *h_blob = nullptr;   // pinned staging of the same
     double *d_partials = nullptr;  // kMaxGrid x 4
-    double *d_out = nullptr;       // 4 doubles
-    unsigned long long *d_counter = nullptr;  // segment dispenser of the walk kernels
-    uint8_t *d_sched = nullptr;    // kMaxSegLenNary
-    double *d_wtab = nullptr;      // kMaxSegLenNary
-    double *d_binom = nullptr;     // kMaxDigits * 256
-    double *h_pinned = nullptr;    // staging: A2 + out
+    double *h_out = nullptr;       // 4 doubles, pinned + mapped: the kernels write the result here
+    double *d_hout = nullptr;      // device alias of h_out
+    unsigned long long *d_counter = nullptr;  // segment dispenser of the walk kernels ...
+    unsigned int *d_done = nullptr;           // ... and their finished-CTA count (self-resetting)
     double last_kernel_ms = -1.0;
     bool ready = false;
-    uint64_t resident_job = 0;     // id of the pq_perm_job whose inputs sit in the buffers
+    uint64_t resident_job = 0;     // id of the pq_perm_job whose inputs sit in the blob
     cudaEvent_t ring0[kTimingRing], ring1[kTimingRing];  // event pairs around the kernels
     uint64_t ring_next = 0;
     // The batched Laplace / sampler path: its device phase runs under `mu` (not

@@ -14,12 +14,12 @@ namespace pqperm {
 // bank (warp-uniform reads through the uniform datapath).
 struct WalkParams {
     const double2 *A2;     // (D+1) x NC: row 0 = pinned row a_0, rows 1..D = 2*a_d
-    const uint8_t *sched;  // [W] digit that moves on the step INTO local index m (n-ary only)
-    const double *wtab;    // [W] (-1)^m * prod_low C(r_i, c_i(m))           (n-ary only)
     const double *binom;   // flattened C(r_d, g) tables, binom_off[d] + g
     double *partials;      // [gridDim.x][4] re_hi, re_lo, im_hi, im_lo
+    double *out4;          // the launch's sum (double-double), written by the last CTA to finish
     double *segsums;       // optional [seg_end - seg_begin][2] per-segment sums
-    unsigned long long *counter;  // next undistributed segment (relative), zeroed per launch
+    unsigned long long *counter;  // next undistributed segment (relative); 0 between launches
+    unsigned int *done;    // CTAs that have stored their partial; 0 between launches
     long long seg_begin;   // segments [seg_begin, seg_end) belong to this launch
     long long seg_end;
     long long W;           // terms per segment = prod_{d<q} radix[d]
@@ -65,7 +65,8 @@ struct LapParams {
     int ldu;
     const double2 *A2;   // packed mode: per-problem matrices
     int perm_only;       // 1: only the full product is wanted (batched permanents)
-    double2 *partials;   // [total CTAs][NCP + 1]
+    int max_D;           // the CTAs' shared matrix area holds (max_D + 1) x NCP entries
+    double *partials;    // [total CTAs][NCP + 1][4]: re hi, re lo, im hi, im lo
     double2 *out;        // [nprob][NCP + 1]: per compact column, then the full product
     int nprob;
 };
@@ -129,6 +130,37 @@ __device__ __forceinline__ void block_reduce_store(dd re, dd im, double *out4)
         out4[1] = r.lo;
         out4[2] = i.hi;
         out4[3] = i.lo;
+    }
+}
+
+// End of a walk kernel: the CTA's partial goes to P.partials; the CTA that
+// finishes LAST sums all partials in index order (fixed tree, so the result is
+// reproducible for a fixed grid), writes the four doubles to P.out4 and re-arms the
+// two counters for the next launch -- no separate reduction kernel, no memset.
+template <int NT>
+__device__ __forceinline__ void finish_grid(const WalkParams &P, dd re, dd im)
+{
+    __shared__ bool s_last;
+    block_reduce_store<NT>(re, im, P.partials + 4 * (size_t)blockIdx.x);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(P.done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last)
+        return;
+    __threadfence();
+    dd r{0.0, 0.0}, i{0.0, 0.0};
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += NT) {
+        const double *q = P.partials + 4 * (size_t)b;
+        dd_add(r, dd{__ldcg(q + 0), __ldcg(q + 1)});
+        dd_add(i, dd{__ldcg(q + 2), __ldcg(q + 3)});
+    }
+    __syncthreads(); // block_reduce_store's scratch is reused
+    block_reduce_store<NT>(r, i, P.out4);
+    if (threadIdx.x == 0) {
+        *P.counter = 0ull;
+        *P.done = 0u;
     }
 }
 

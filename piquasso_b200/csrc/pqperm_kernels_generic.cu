@@ -1,5 +1,5 @@
-// pqperm_kernels_generic.cu -- instantiations of the generic n-ary walk, the
-// partial-sum reduction and the DFMA throughput probe.
+// pqperm_kernels_generic.cu -- instantiations of the generic n-ary walk and the
+// DFMA throughput probe.
 #include "pqperm_launch_impl.cuh"
 
 namespace pqperm {
@@ -48,25 +48,6 @@ cudaError_t launch_generic(int ncp, bool binary, bool unitcols, const WalkParams
     default:
         return cudaErrorInvalidValue;
     }
-}
-
-// ---- final reduction of the per-block partials -----------------------------
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const double *partials, int n,
-                                                             double *out4)
-{
-    dd re{0.0, 0.0}, im{0.0, 0.0};
-    for (int i = threadIdx.x; i < n; i += 256) {
-        dd_add(re, dd{partials[4 * i + 0], partials[4 * i + 1]});
-        dd_add(im, dd{partials[4 * i + 2], partials[4 * i + 3]});
-    }
-    block_reduce_store<256>(re, im, out4);
-}
-
-cudaError_t launch_reduce_partials(const double *partials, int n, double *out4,
-                                   cudaStream_t stream)
-{
-    reduce_partials_kernel<<<1, 256, 0, stream>>>(partials, n, out4);
-    return cudaGetLastError();
 }
 
 // ---- DFMA probe: the FP64 roofline denominator, measured -------------------

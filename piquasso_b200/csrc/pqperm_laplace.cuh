@@ -7,16 +7,28 @@
 //   out_l * 2^(N-1) = sum_offset (-1)^{sum g} prod_d C(r_d,g_d)
 //                       * s_l^{c_l-1} prod_{k != l} s_k^{c_k}
 // The reference recomputes each of the C products from scratch (O(C*M) per
-// term); here one suffix pass + one prefix pass give all of them: per column two
-// complex multiplies and one complex multiply-add into the accumulator (the
-// term weight rides in the prefix chain), 14 FP64 instructions with the row-sum
-// update.
+// term).  Here all leave-one-out products of a term come from ONE balanced
+// product tree over the lane's columns (unit column multiplicities, what the
+// sampler issues): an up-sweep stores the product of every subtree, a
+// down-sweep hands every node the product of everything outside it, and a
+// leaf's outside product is accumulated by a complex FMA
+//   acc_l += outside(parent) * inside(sibling)
+// -- per column two complex multiplies and one complex multiply-add, 14 FP64
+// instructions with the row-sum update, exactly what a suffix/prefix pass
+// costs, but with a dependency depth of 2 log2(C) multiplies instead of 2 C:
+// the FP64 pipe sees C/2 independent chains instead of two.  (Column
+// multiplicities > 1 keep the chunked suffix/prefix passes.)
 //
 // Batch layout: one launch walks many independent problems (the sampler's
 // (shot, photon) problems).  A CTA works on one problem; S adjacent lanes
 // ("group") share one Gray segment and split the columns (lane h owns columns
-// h, h+S, ...), so that row sums, suffix products and accumulators of up to 64
+// h, h+S, ...), so that row sums, subtree products and accumulators of up to 64
 // columns stay in registers.
+//
+// Accumulation: a thread sums the terms of one segment (<= 256) in plain FP64
+// registers and then folds them into its double-double totals, which live in
+// shared memory ([slot][thread], conflict-free); warp, CTA and cross-CTA
+// reductions stay double-double (TwoSum) up to the final scaling.
 #pragma once
 
 #include "pqperm_device.cuh"
@@ -33,18 +45,156 @@ __device__ __forceinline__ double small_binom(int n, int k)
     return r;
 }
 
+// ---- balanced product tree over the N columns of a lane ------------------------
+// Node [LO, HI) with HI - LO >= 2 splits at MID = (LO + HI) / 2; every boundary
+// between two adjacent leaves is the split point of exactly one node, so the
+// product of node [LO, HI) is stored at index MID of (nr, ni).
+
+// product of the subtree [LO, HI): a leaf's row sum or a stored node product
+template <int LO, int HI, int N>
+__device__ __forceinline__ void tree_value(const double (&sr)[N], const double (&si)[N],
+                                           const double (&nr)[N], const double (&ni)[N],
+                                           double &vr, double &vi)
+{
+    if constexpr (HI - LO == 1) {
+        vr = sr[LO];
+        vi = si[LO];
+    } else {
+        vr = nr[(LO + HI) / 2];
+        vi = ni[(LO + HI) / 2];
+    }
+}
+
+// up-sweep: products of all internal nodes below [LO, HI)
+template <int LO, int HI, int N>
+__device__ __forceinline__ void tree_up(const double (&sr)[N], const double (&si)[N],
+                                        double (&nr)[N], double (&ni)[N])
+{
+    if constexpr (HI - LO >= 2) {
+        constexpr int MID = (LO + HI) / 2;
+        tree_up<LO, MID, N>(sr, si, nr, ni);
+        tree_up<MID, HI, N>(sr, si, nr, ni);
+        double lr, li, rr, ri;
+        tree_value<LO, MID, N>(sr, si, nr, ni, lr, li);
+        tree_value<MID, HI, N>(sr, si, nr, ni, rr, ri);
+        nr[MID] = __fma_rn(lr, rr, -(li * ri));
+        ni[MID] = __fma_rn(lr, ri, li * rr);
+    }
+}
+
+// down-sweep from node [LO, HI) whose outside product (term weight included) is
+// (our, oui) -- real when REALW.  A leaf child receives outside * inside(sibling)
+// straight into its accumulator; its row sum is then moved to the NEXT term
+// (s += sg * row), which is the last thing this term needs it for.
+template <int LO, int HI, int N, int S, bool REALW>
+__device__ __forceinline__ void tree_down(double (&sr)[N], double (&si)[N],
+                                          const double (&nr)[N], const double (&ni)[N],
+                                          double our, double oui, double (&accr)[N],
+                                          double (&acci)[N], const double2 *row, double sg)
+{
+    static_assert(HI - LO >= 2, "tree_down needs an internal node");
+    constexpr int MID = (LO + HI) / 2;
+    constexpr bool LLEAF = (MID - LO == 1), RLEAF = (HI - MID == 1);
+    double lr, li, rr, ri;
+    tree_value<LO, MID, N>(sr, si, nr, ni, lr, li);
+    tree_value<MID, HI, N>(sr, si, nr, ni, rr, ri);
+    double xlr = 0.0, xli = 0.0, xrr = 0.0, xri = 0.0;
+    if constexpr (LLEAF) {
+        if (REALW) {
+            accr[LO] = __fma_rn(our, rr, accr[LO]);
+            acci[LO] = __fma_rn(our, ri, acci[LO]);
+        } else {
+            cfma(accr[LO], acci[LO], our, oui, rr, ri);
+        }
+    } else {
+        if (REALW) {
+            xlr = our * rr;
+            xli = our * ri;
+        } else {
+            xlr = our;
+            xli = oui;
+            cmul(xlr, xli, rr, ri);
+        }
+    }
+    if constexpr (RLEAF) {
+        if (REALW) {
+            accr[MID] = __fma_rn(our, lr, accr[MID]);
+            acci[MID] = __fma_rn(our, li, acci[MID]);
+        } else {
+            cfma(accr[MID], acci[MID], our, oui, lr, li);
+        }
+    } else {
+        if (REALW) {
+            xrr = our * lr;
+            xri = our * li;
+        } else {
+            xrr = our;
+            xri = oui;
+            cmul(xrr, xri, lr, li);
+        }
+    }
+    if constexpr (LLEAF) {
+        const double2 a = row[LO * S];
+        sr[LO] = __fma_rn(sg, a.x, sr[LO]);
+        si[LO] = __fma_rn(sg, a.y, si[LO]);
+    }
+    if constexpr (RLEAF) {
+        const double2 a = row[MID * S];
+        sr[MID] = __fma_rn(sg, a.x, sr[MID]);
+        si[MID] = __fma_rn(sg, a.y, si[MID]);
+    }
+    if constexpr (!LLEAF)
+        tree_down<LO, MID, N, S, false>(sr, si, nr, ni, xlr, xli, accr, acci, row, sg);
+    if constexpr (!RLEAF)
+        tree_down<MID, HI, N, S, false>(sr, si, nr, ni, xrr, xri, accr, acci, row, sg);
+}
+
+// Product of the OTHER lanes' totals in a group of S lanes (butterfly: T = product
+// of my sub-group, O = the same without me; log2 S shuffle rounds).
+template <int S>
+__device__ __forceinline__ void others_product(double lr, double li, double &olr, double &oli)
+{
+    double tr = lr, ti = li;
+    olr = 1.0;
+    oli = 0.0;
+#pragma unroll
+    for (int x = 1; x < S; x <<= 1) {
+        const double pr = __shfl_xor_sync(0xffffffffu, tr, x);
+        const double pi = __shfl_xor_sync(0xffffffffu, ti, x);
+        if (x == 1) {
+            olr = pr;
+            oli = pi;
+        } else {
+            cmul(olr, oli, pr, pi);
+        }
+        if (2 * x < S)
+            cmul(tr, ti, pr, pi);
+    }
+}
+
+// Slots of a thread's double-double totals in shared memory: column j uses
+// slots 4j .. 4j+3 (re hi, re lo, im hi, im lo), the full product 4 NCL .. 4 NCL+3.
+__device__ __forceinline__ void dd_fold(double *tot, int slot, int nt, double v)
+{
+    // tot[slot] (hi), tot[slot + 1] (lo) += v   (TwoSum)
+    double *hi = tot + (size_t)slot * nt, *lo = hi + nt;
+    const double a = *hi;
+    const double s = a + v;
+    const double bb = s - a;
+    const double e = (a - (s - bb)) + (v - bb);
+    *hi = s;
+    *lo += e;
+}
+
 template <int NCL, int S, bool UNITCOLS>
 __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapParams P)
 {
     constexpr int NCP = NCL * S;
     constexpr int NT = kLapThreads;
-    // independent suffix / prefix chains per lane.  Two are enough once the
-    // next term's row-sum update is interleaved with the prefix pass (measured
-    // on B200: k=25 walk 0.467 ms per 2^23 terms with 3 chunks, 0.453 with 2);
-    // every extra chunk costs 2-3 complex multiplies per term.
+    // chunked suffix / prefix chains of the general (column multiplicity) flavour
     constexpr int CH = NCL >= 4 ? 2 : 1;
     constexpr int CLEN = (NCL + CH - 1) / CH;              // longest chunk
-    extern __shared__ double2 smA[];              // (D+1) x NCP
+    extern __shared__ double2 smA[];              // (D+1) x NCP, then the totals
     __shared__ double s_wtab[kLapMaxSegLen];
     __shared__ uint8_t s_sched[kLapMaxSegLen];
     __shared__ int s_prob;
@@ -66,6 +216,8 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
     const uint8_t *colmult = P.wide ? P.wide[s_prob].colmult : Q.colmult;
     const uint16_t *colmode = P.wide ? P.wide[s_prob].colmode : Q.colmode;
     const int D = Q.D, q = Q.q, W = Q.W;
+    // this thread's double-double totals: tot[slot * NT]
+    double *tot = reinterpret_cast<double *>(smA + (size_t)(P.max_D + 1) * NCP) + threadIdx.x;
     {
         const int nelem = (D + 1) * NCP;
         if (P.U) {
@@ -106,16 +258,22 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
             s_sched[m] = (uint8_t)(p < 0 ? 0 : p);
             s_wtab[m] = w;
         }
+#pragma unroll 4
+        for (int k = 0; k < 4 * NCL + 4; k++)
+            tot[k * NT] = 0.0;
     }
     __syncthreads();
 
     const int h = threadIdx.x % S;                 // lane within the group
     const int groups_per_block = NT / S;
     const long long gstride = (long long)Q.nblocks * groups_per_block;
+    // sums of the current segment(s), plain FP64; folded into `tot` every segment
+    // (every kLapFoldTerms terms when the segments are shorter)
     double accr[NCL], acci[NCL], fullr = 0.0, fulli = 0.0;
 #pragma unroll
     for (int j = 0; j < NCL; j++)
         accr[j] = acci[j] = 0.0;
+    int unfolded = 0;
 
     // All lanes of a warp run the same number of iterations (the group shuffles
     // below need the full warp); lanes past the last segment redo the last one
@@ -184,10 +342,9 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
         const double factor = valid ? (odd ? -bin : bin) : 0.0;
 
         // ---- walk
-        // The move INTO term m+1 is applied column by column at the end of term
-        // m's prefix pass (right after the last use of s_j): its 2*NCL independent
-        // FMAs and the row loads then fill the latency gaps of the dependent
-        // prefix chains instead of sitting in front of the suffix pass.
+        // The move INTO term m+1 is applied column by column as soon as term m has
+        // no further use for s_j: its 2*NCL independent FMAs and the row loads fill
+        // latency gaps of the product chains instead of sitting in front of them.
         int p_next = W > 1 ? s_sched[1] : 0;
         for (int m = 0; m < W; ++m) {
             const double w = factor * s_wtab[m];
@@ -201,7 +358,57 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
             // present, finite) times sg = 0 leaves s untouched
             const double2 *row = smA + (more ? p + 1 : 0) * NCP + h;
 
-            // ---- all C leave-one-out products of this term -------------------
+            if constexpr (UNITCOLS) {
+                // ---- product tree ---------------------------------------------------
+                double nr[NCL], ni[NCL];
+                tree_up<0, NCL, NCL>(sr, si, nr, ni);
+                double lr, li; // product of this lane's columns
+                tree_value<0, NCL, NCL>(sr, si, nr, ni, lr, li);
+                double olr = 1.0, oli = 0.0; // other lanes (S > 1 only)
+                if (S > 1)
+                    others_product<S>(lr, li, olr, oli);
+                if (P.perm_only) {
+                    // batched permanents: the product of ALL columns is the term
+                    if (S > 1)
+                        cmul(lr, li, olr, oli);
+                    fullr = __fma_rn(w, lr, fullr);
+                    fulli = __fma_rn(w, li, fulli);
+#pragma unroll
+                    for (int j = 0; j < NCL; j++) {
+                        const double2 a = row[j * S];
+                        sr[j] = __fma_rn(sg, a.x, sr[j]);
+                        si[j] = __fma_rn(sg, a.y, si[j]);
+                    }
+                    continue;
+                }
+                if (S > 1) {
+                    // outside of the lane's root: w * other lanes; w * the product of
+                    // ALL columns is what a c_l = 0 column gets
+                    const double wor = w * olr, woi = w * oli;
+                    cfma(fullr, fulli, wor, woi, lr, li);
+                    if constexpr (NCL >= 2) {
+                        tree_down<0, NCL, NCL, S, false>(sr, si, nr, ni, wor, woi, accr, acci,
+                                                         row, sg);
+                    } else {
+                        accr[0] += wor;
+                        acci[0] += woi;
+                    }
+                } else {
+                    fullr = __fma_rn(w, lr, fullr);
+                    fulli = __fma_rn(w, li, fulli);
+                    if constexpr (NCL >= 2)
+                        tree_down<0, NCL, NCL, S, true>(sr, si, nr, ni, w, 0.0, accr, acci, row,
+                                                        sg);
+                    else
+                        accr[0] += w;
+                }
+                if constexpr (NCL == 1) {
+                    const double2 a = row[0];
+                    sr[0] = __fma_rn(sg, a.x, sr[0]);
+                    si[0] = __fma_rn(sg, a.y, si[0]);
+                }
+            } else {
+            // ---- column multiplicities: chunked suffix / prefix passes ------------
             // The lane's columns are cut into CH chunks whose suffix / prefix
             // chains are independent (interleaved below so that the FP64 pipe
             // sees CH chains at once); the term weight and the product of
@@ -217,11 +424,9 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                     const int j = j0 + i;
                     if (j < j1) {
                         double tr = sr[j], ti = si[j];
-                        if (!UNITCOLS) {
-                            const int cm = colmult[j * S + h];
-                            for (int k = 1; k < cm; k++)
-                                cmul(tr, ti, sr[j], si[j]);
-                        }
+                        const int cm = colmult[j * S + h];
+                        for (int k = 1; k < cm; k++)
+                            cmul(tr, ti, sr[j], si[j]);
                         if (j + 1 < j1)
                             cmul(tr, ti, sufr[j + 1], sufi[j + 1]);
                         sufr[j] = tr;
@@ -229,66 +434,25 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                     }
                 }
             }
-            // lane-local leave-one-chunk-out products out_c = prod_{c' != c} T_c'
-            // (T_c = suf[first column of chunk c]) and the lane total
+            // lane-local leave-one-chunk-out products and the lane total (CH <= 2)
             double outr[CH], outi[CH], lr, li;
-            {
-                double pTr[CH], pTi[CH]; // prod_{c' < c} T_c'   (c >= 1)
-                double sTr[CH], sTi[CH]; // prod_{c' > c} T_c'   (c <= CH-2)
-#pragma unroll
-                for (int c = 1; c < CH; c++) {
-                    const int f = (NCL * (c - 1)) / CH;
-                    pTr[c] = sufr[f];
-                    pTi[c] = sufi[f];
-                    if (c > 1)
-                        cmul(pTr[c], pTi[c], pTr[c - 1], pTi[c - 1]);
-                }
-#pragma unroll
-                for (int c = CH - 2; c >= 0; c--) {
-                    const int f = (NCL * (c + 1)) / CH;
-                    sTr[c] = sufr[f];
-                    sTi[c] = sufi[f];
-                    if (c < CH - 2)
-                        cmul(sTr[c], sTi[c], sTr[c + 1], sTi[c + 1]);
-                }
-#pragma unroll
-                for (int c = 0; c < CH; c++) {
-                    if (CH == 1) {
-                        outr[c] = 1.0;
-                        outi[c] = 0.0;
-                    } else if (c == 0) {
-                        outr[c] = sTr[0];
-                        outi[c] = sTi[0];
-                    } else if (c == CH - 1) {
-                        outr[c] = pTr[c];
-                        outi[c] = pTi[c];
-                    } else {
-                        outr[c] = pTr[c];
-                        outi[c] = pTi[c];
-                        cmul(outr[c], outi[c], sTr[c], sTi[c]);
-                    }
-                }
-                lr = sufr[0];
-                li = sufi[0];
-                if (CH > 1)
-                    cmul(lr, li, outr[0], outi[0]);
+            lr = sufr[0];
+            li = sufi[0];
+            if (CH == 1) {
+                outr[0] = 1.0;
+                outi[0] = 0.0;
+            } else {
+                constexpr int F1 = NCL / 2; // first column of chunk 1
+                outr[0] = sufr[F1];
+                outi[0] = sufi[F1];
+                outr[CH - 1] = sufr[0];
+                outi[CH - 1] = sufi[0];
+                cmul(lr, li, outr[0], outi[0]);
             }
             double olr = 1.0, oli = 0.0; // other lanes (S > 1 only)
-            if (S > 1) {
-#pragma unroll
-                for (int x = 1; x < S; x++) {
-                    const double orr = __shfl_xor_sync(0xffffffffu, lr, x);
-                    const double oi = __shfl_xor_sync(0xffffffffu, li, x);
-                    if (x == 1) {
-                        olr = orr;
-                        oli = oi;
-                    } else {
-                        cmul(olr, oli, orr, oi);
-                    }
-                }
-            }
+            if (S > 1)
+                others_product<S>(lr, li, olr, oli);
             if (P.perm_only) {
-                // batched permanents: the product of ALL columns is the term
                 if (S > 1)
                     cmul(lr, li, olr, oli);
                 fullr = __fma_rn(w, lr, fullr);
@@ -302,8 +466,7 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                 continue;
             }
             // start value of every chunk's prefix chain: w * other lanes * out_c.
-            // Carrying w in the chain turns the accumulation into a complex FMA
-            // (acc += pre * suf: 4 DFMA instead of a complex multiply + 2 DFMA).
+            // Carrying w in the chain turns the accumulation into a complex FMA.
             double prer[CH], prei[CH];
             if (S > 1) {
                 const double wor = w * olr, woi = w * oli;
@@ -314,7 +477,6 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                     if (CH > 1)
                         cmul(prer[c], prei[c], outr[c], outi[c]);
                 }
-                // w * the product of ALL columns: what a c_l = 0 column gets
                 cfma(fullr, fulli, wor, woi, lr, li);
             } else {
 #pragma unroll
@@ -334,11 +496,9 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                     const int j = j0 + i;
                     if (j < j1) {
                         double pr = prer[c], pi = prei[c];
-                        if (!UNITCOLS) {
-                            const int cm = colmult[j * S + h];
-                            for (int k = 1; k < cm; k++)
-                                cmul(pr, pi, sr[j], si[j]); // pre * s_j^{c_j - 1}
-                        }
+                        const int cm = colmult[j * S + h];
+                        for (int k = 1; k < cm; k++)
+                            cmul(pr, pi, sr[j], si[j]); // pre * s_j^{c_j - 1}
                         if (j + 1 < j1) {
                             cfma(accr[j], acci[j], pr, pi, sufr[j + 1], sufi[j + 1]);
                             cmul(pr, pi, sr[j], si[j]); // next start: pre * s_j^{c_j}
@@ -355,50 +515,67 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                     }
                 }
             }
+            } // general flavour
+        }
+        // ---- fold the segment sums into the double-double totals
+        unfolded += W;
+        if (unfolded >= kLapFoldTerms) {
+            unfolded = 0;
+#pragma unroll
+            for (int j = 0; j < NCL; j++) {
+                dd_fold(tot, 4 * j, NT, accr[j]);
+                dd_fold(tot, 4 * j + 2, NT, acci[j]);
+                accr[j] = acci[j] = 0.0;
+            }
+            dd_fold(tot, 4 * NCL, NT, fullr);
+            dd_fold(tot, 4 * NCL + 2, NT, fulli);
+            fullr = fulli = 0.0;
         }
     }
 
-    // ---- CTA reduction: lanes with equal h hold the same columns
-    __shared__ double red[(NT / 32) * (NCP + 1) * 2];
-#pragma unroll
-    for (int j = 0; j < NCL; j++) {
+    // ---- CTA reduction (double-double): lanes with equal h hold the same columns.
+    // Each warp reduces its totals with shuffles and parks the result in the slots
+    // of its lanes 0..S-1; after the barrier NCP + 1 threads add the four warps.
+    auto warp_reduce = [&](int j, double restr, double resti) {
+        dd re{tot[(4 * j) * NT], tot[(4 * j + 1) * NT]};
+        dd im{tot[(4 * j + 2) * NT], tot[(4 * j + 3) * NT]};
+        dd_add(re, restr); // what has not been folded yet
+        dd_add(im, resti);
 #pragma unroll
         for (int delta = 16; delta >= S; delta >>= 1) {
-            accr[j] += __shfl_down_sync(0xffffffffu, accr[j], delta);
-            acci[j] += __shfl_down_sync(0xffffffffu, acci[j], delta);
+            dd_add(re, dd_shfl_down(re, delta));
+            dd_add(im, dd_shfl_down(im, delta));
         }
-    }
+        tot[(4 * j) * NT] = re.hi;
+        tot[(4 * j + 1) * NT] = re.lo;
+        tot[(4 * j + 2) * NT] = im.hi;
+        tot[(4 * j + 3) * NT] = im.lo;
+    };
 #pragma unroll
-    for (int delta = 16; delta >= S; delta >>= 1) {
-        fullr += __shfl_down_sync(0xffffffffu, fullr, delta);
-        fulli += __shfl_down_sync(0xffffffffu, fulli, delta);
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane < S) {
-        double *dst = red + warp * (NCP + 1) * 2;
-#pragma unroll
-        for (int j = 0; j < NCL; j++) {
-            dst[(j * S + lane) * 2] = accr[j];
-            dst[(j * S + lane) * 2 + 1] = acci[j];
-        }
-        if (lane == 0) {
-            dst[NCP * 2] = fullr;
-            dst[NCP * 2 + 1] = fulli;
-        }
-    }
+    for (int j = 0; j < NCL; j++)
+        warp_reduce(j, accr[j], acci[j]);
+    warp_reduce(NCL, fullr, fulli);
     __syncthreads();
+    const double *tot0 = reinterpret_cast<const double *>(smA + (size_t)(P.max_D + 1) * NCP);
     for (int k = threadIdx.x; k < NCP + 1; k += NT) {
-        double re = 0.0, im = 0.0;
+        // compact column k = j * S + lane; the full product sits in lane 0's slots
+        const int j = k < NCP ? k / S : NCL, lane = k < NCP ? k % S : 0;
+        dd re{0.0, 0.0}, im{0.0, 0.0};
         for (int w = 0; w < NT / 32; w++) {
-            re += red[(w * (NCP + 1) + k) * 2];
-            im += red[(w * (NCP + 1) + k) * 2 + 1];
+            const double *src = tot0 + w * 32 + lane;
+            dd_add(re, dd{src[(4 * j) * NT], src[(4 * j + 1) * NT]});
+            dd_add(im, dd{src[(4 * j + 2) * NT], src[(4 * j + 3) * NT]});
         }
-        P.partials[(size_t)blockIdx.x * (NCP + 1) + k] = make_double2(re, im);
+        double *dst = P.partials + ((size_t)blockIdx.x * (NCP + 1) + k) * 4;
+        dst[0] = re.hi;
+        dst[1] = re.lo;
+        dst[2] = im.hi;
+        dst[3] = im.lo;
     }
 }
 
-// One warp per problem: sum the problem's CTA partials in CTA order, scale by
-// 2^-(sum_rows - 1) (src/permanent_laplace.cpp:226-235).
+// One warp per problem: sum the problem's CTA partials (double-double) in CTA
+// order, scale by 2^-(sum_rows - 1) (src/permanent_laplace.cpp:226-235).
 static __global__ void __launch_bounds__(128) laplace_reduce_kernel(const LapParams P, int ncp1)
 {
     const int prob = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -407,13 +584,14 @@ static __global__ void __launch_bounds__(128) laplace_reduce_kernel(const LapPar
     const LapProblem &Q = P.prob[prob];
     const double scale = scalbn(1.0, -Q.exp2);
     for (int k = threadIdx.x & 31; k < ncp1; k += 32) {
-        double re = 0.0, im = 0.0;
+        dd re{0.0, 0.0}, im{0.0, 0.0};
         for (int b = 0; b < Q.nblocks; b++) {
-            const double2 v = P.partials[(size_t)(Q.first_block + b) * ncp1 + k];
-            re += v.x;
-            im += v.y;
+            const double *v = P.partials + ((size_t)(Q.first_block + b) * ncp1 + k) * 4;
+            dd_add(re, dd{v[0], v[1]});
+            dd_add(im, dd{v[2], v[3]});
         }
-        P.out[(size_t)prob * ncp1 + k] = make_double2(re * scale, im * scale);
+        P.out[(size_t)prob * ncp1 + k] =
+            make_double2((re.hi + re.lo) * scale, (im.hi + im.lo) * scale);
     }
 }
 

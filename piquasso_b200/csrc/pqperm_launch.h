@@ -23,14 +23,13 @@ cudaError_t launch_generic(int ncp, bool binary, bool unitcols, const WalkParams
                            int num_sms, int max_grid, cudaStream_t stream,
                            LaunchInfo *info);
 
-// Binary hypercube walk (kernel 2).  `d_A2` ((P.D+1) x nc double2, device
-// memory) is copied into the kernel's __constant__ matrix on `stream` first.
-cudaError_t launch_binary(int nc, int B, const WalkParams &P, const double2 *d_A2,
-                          int num_sms, int max_grid, cudaStream_t stream, LaunchInfo *info);
-
-// out4[k] (+)= sum over n partial quadruples (double-double), one block.
-cudaError_t launch_reduce_partials(const double *partials, int n, double *out4,
-                                   cudaStream_t stream);
+// Binary hypercube walk (kernel 2).  With `h_A2` (host, (P.D+1) x nc double2) and
+// nc <= kBinMaxParamCols the matrix rides in the kernel's parameter block;
+// otherwise `d_A2` (device, same layout) is copied into the kernel's __constant__
+// matrix on `stream` first.
+cudaError_t launch_binary(int nc, int B, const WalkParams &P, const double *h_A2,
+                          const double2 *d_A2, int num_sms, int max_grid, cudaStream_t stream,
+                          LaunchInfo *info);
 
 // DFMA throughput probe: returns flops executed, time via events by caller.
 cudaError_t launch_dfma_probe(int num_sms, int iters, double *sink, cudaStream_t stream,

@@ -12,16 +12,29 @@ constexpr int kMaxLowDigits = 24;       // digits walked inside one segment
 constexpr int kMaxMultiplicity = 254;   // radix r+1 is stored in a byte
 constexpr int kBinMinCols = 8;          // narrowest binary constant-bank kernel
 constexpr int kBinMaxCols = 48;         // widest binary constant-bank kernel
+constexpr int kBinMaxParamCols = 44;     // widest binary matrix that rides in the kernel parameter block
 constexpr int kBinMaxBlockExp = 4;      // kernel 2: at most 2^4 terms per block (instantiated for C <= 32)
 // kernel 2: log2 of the terms per block for nc columns (register budget:
 // 4*nc for the row sums + 4 * 2^B for the running products)
 inline int binary_block_exponent(int /*nc*/) { return 3; }  // measured best for 20 <= nc <= 48
-constexpr int kBinMinDigitsAuto = 25;   // below 2^25 terms the generic walk's lower setup cost wins
+// Below 2^kBinMinDigitsAuto terms the generic walk is used.  (Was 25 while the
+// binary walk needed its matrix uploaded into a __constant__ array first; with the
+// matrix riding in the kernel parameters its setup cost is that of any launch.)
+constexpr int kBinMinDigitsAuto = 12;
 constexpr int64_t kMaxSegLenBinary = INT64_C(1) << 14;
-constexpr int64_t kMaxSegLenNary = INT64_C(1) << 12;
+constexpr int64_t kMaxSegLenNary = INT64_C(1) << 10;  // step tables live in shared memory (9 KB)
 
 constexpr int kLapMaxSegLen = 256;     // Laplace: terms per segment (tables in shared memory)
 constexpr int kLapThreads = 128;
+constexpr int kLapFoldTerms = 64;      // Laplace: plain-FP64 terms between double-double folds
+// Dynamic shared memory of one CTA of the Laplace walk: the (D+1) x NCP complex
+// matrix, then every thread's double-double totals (4 doubles per column of the
+// lane plus 4 for the full product).  Must fit beside ~2.3 KB of static tables.
+constexpr size_t kLapSmemLimit = 224 * 1024;
+inline size_t lap_smem_bytes(int D, int S, int NCL)
+{
+    return (size_t)(D + 1) * S * NCL * 16 + (size_t)(4 * NCL + 4) * kLapThreads * 8;
+}
 
 // Lane split of the Laplace walk for nc active columns: S lanes per Gray
 // segment, NCL columns per lane (S * NCL >= nc).

@@ -157,7 +157,10 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
 
     // ---- where to cut the digits --------------------------------------------
     // cost(q) ~ waves(q) * (seed + W(q) * step); see DESIGN.md "partition".
-    const double regs = 4.0 * plan.NCP + 48.0;
+    // registers per thread: the binary walk's are known (ptxas, 64-thread CTAs)
+    const double regs = plan.kernel == 2
+                            ? (plan.NC <= 16 ? 128.0 : (plan.NC <= 26 ? 168.0 : 255.0))
+                            : 4.0 * plan.NCP + 48.0;
     double resident = std::floor(65536.0 / regs / 64.0) * 64.0;
     resident = std::max(64.0, std::min(2048.0, resident)) * opt.num_sms;
     const double step = 2.0 * plan.NCP + 4.0 * plan.M + 2.0;
@@ -210,27 +213,9 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
         for (int g = 0; g <= plan.mult[d]; g++)
             plan.binom.push_back(binom_d(plan.mult[d], g));
     }
-    if (!(plan.binary && plan.unitcols)) {
-        // step m-1 -> m of the low counter: which digit moves, and the weight
-        // (-1)^m prod_{d<q} C(r_d, c_d(m)) (C(r,g) = C(r,r-g): the reflection
-        // of a digit does not change its binomial).
-        plan.sched.assign((size_t)plan.W, 0);
-        plan.wtab.assign((size_t)plan.W, 1.0);
-        std::vector<int> chain(std::max(plan.q, 1), 0);
-        for (int64_t m = 1; m < plan.W; m++) {
-            int p = 0;
-            while (chain[p] == plan.mult[p]) {
-                chain[p] = 0;
-                p++;
-            }
-            chain[p]++;
-            plan.sched[(size_t)m] = (uint8_t)p;
-            double w = (m & 1) ? -1.0 : 1.0;
-            for (int d = 0; d < plan.q; d++)
-                w *= plan.binom[plan.binom_off[d] + chain[d]];
-            plan.wtab[(size_t)m] = w;
-        }
-    }
+    // (the step tables of the low counter -- which digit moves into local index m
+    // and the weight (-1)^m prod_{d<q} C(r_d, c_d(m)) -- are built on the device by
+    // every CTA, pqperm_walk.cuh)
 
     // ---- compacted, pre-doubled matrix ----------------------------------------
     if (A) {

@@ -45,8 +45,6 @@ struct Plan {
     int64_t nseg = 1;         // segments
     int kernel = 1;           // 1 generic, 2 binary constant-bank
     int B = 0;                // kernel 2: 2^B terms (one hypercube of the low digits) per block
-    std::vector<uint8_t> sched;     // [W]   (generic, non-binary)
-    std::vector<double> wtab;       // [W]
     std::vector<double> binom;      // flattened C(r_d, g)
     std::vector<int> binom_off;     // [D]
 };

@@ -187,15 +187,36 @@ template <int NC, bool BINARY, bool UNITCOLS, int NT>
 __global__ void __launch_bounds__(NT) perm_walk_generic(const __grid_constant__ WalkParams P)
 {
     extern __shared__ double2 smA[];
+    // step tables of the low counter (n-ary only), built by the CTA itself: the
+    // digit moved on the step into m and (-1)^m prod_{d<q} C(r_d, c_d(m)).  In
+    // shared memory they cost one LDS per step; nothing is uploaded for them.
+    __shared__ double s_wtab[BINARY ? 1 : kMaxSegLenNary];
+    __shared__ uint8_t s_sched[BINARY ? 1 : kMaxSegLenNary];
+    const int W = (int)P.W;
     {
         const int nelem = (P.D + 1) * NC;
         for (int i = threadIdx.x; i < nelem; i += NT)
             smA[i] = P.A2[i];
+        if (!BINARY) {
+            for (int m = threadIdx.x; m < W; m += NT) {
+                int rest = m, p = -1;
+                double w = (m & 1) ? -1.0 : 1.0;
+                for (int d = 0; d < P.q; d++) {
+                    const int L = P.radix[d];
+                    const int c = rest % L;
+                    rest /= L;
+                    if (p < 0 && c != 0)
+                        p = d;
+                    w *= P.binom[P.binom_off[d] + c];
+                }
+                s_sched[m] = (uint8_t)(p < 0 ? 0 : p);
+                s_wtab[m] = w;
+            }
+        }
     }
     __syncthreads();
 
     dd totre{0.0, 0.0}, totim{0.0, 0.0};
-    const int W = (int)P.W;
     for (;;) {
         // dynamic distribution: a warp takes the next 32 segments (see next_batch)
         const long long seg = next_batch(P);
@@ -210,6 +231,7 @@ __global__ void __launch_bounds__(NT) perm_walk_generic(const __grid_constant__ 
 
         dd segre{0.0, 0.0}, segim{0.0, 0.0};
         constexpr int CHUNK = 64;
+        int p_next = (!BINARY && W > 1) ? s_sched[1] : 0; // fetched one step ahead
         for (int m0 = 0; m0 < W; m0 += CHUNK) {
             const int m1 = min(W, m0 + CHUNK);
             double accr = 0.0, acci = 0.0;
@@ -221,8 +243,9 @@ __global__ void __launch_bounds__(NT) perm_walk_generic(const __grid_constant__ 
                         p = __ffs(m) - 1;
                         w = (m & 1) ? -1.0 : 1.0;
                     } else {
-                        p = P.sched[m];
-                        w = P.wtab[m];
+                        p = p_next;
+                        p_next = s_sched[m + 1 < W ? m + 1 : m];
+                        w = s_wtab[m];
                     }
                     const double sg = ((dirmask >> p) & 1u) ? 1.0 : -1.0;
                     dirmask ^= (1u << p) - 1u;
@@ -251,10 +274,9 @@ __global__ void __launch_bounds__(NT) perm_walk_generic(const __grid_constant__ 
         dd_add(totre, segre);
         dd_add(totim, segim);
     }
-    block_reduce_store<NT>(totre, totim, P.partials + 4 * (size_t)blockIdx.x);
+    finish_grid<NT>(P, totre, totim);
 }
 
-#ifdef PQ_BINARY_CONST_MATRIX
 #ifndef PQ_COL_CHUNK
 #define PQ_COL_CHUNK 8
 #endif
@@ -292,11 +314,15 @@ __device__ __forceinline__ void sched_fence(double (&pr)[NP], double (&pi)[NP],
 // FP64 instructions per term: 2C (vertex adds + corner move) + 4(C-1)
 // (products) + 2 (signed sum)  =  6C - 2, as in the reference's hot loop
 // (src/permanent.cpp:218-250) but with every operand warp-uniform.
+//
+// `cA` is the (D+1) x NC doubled matrix in a CONSTANT bank: either the kernel's own
+// parameter block (perm_walk_binary_pm: the matrix rides in the launch, nothing is
+// uploaded beforehand) or the translation unit's __constant__ array (perm_walk_binary,
+// for the widths whose matrix does not fit the 32 KB parameter space).
 template <int NC, int B, int NT>
-__global__ void __launch_bounds__(NT) perm_walk_binary(const __grid_constant__ WalkParams P)
+__device__ __forceinline__ void binary_walk_body(const WalkParams &P, const double2 *cA)
 {
     constexpr int NP = 1 << B;
-    const double2 *cA = PQ_BINARY_CONST_MATRIX;
 
     dd totre{0.0, 0.0}, totim{0.0, 0.0};
     const int nblk = (int)(P.W >> B);
@@ -420,7 +446,30 @@ __global__ void __launch_bounds__(NT) perm_walk_binary(const __grid_constant__ W
             }
         }
     }
-    block_reduce_store<NT>(totre, totim, P.partials + 4 * (size_t)blockIdx.x);
+    finish_grid<NT>(P, totre, totim);
+}
+
+// Binary problems with unit columns have D + 1 = NC rows: an NC x NC matrix.
+template <int NC>
+struct WalkParamsM {
+    WalkParams P;
+    double2 m[NC * NC];
+};
+// the widest such matrix must fit the kernel parameter space (32764 bytes, CUDA >= 12.1)
+static_assert(sizeof(WalkParamsM<kBinMaxParamCols>) <= 32764, "parameter block too large");
+
+template <int NC, int B, int NT>
+__global__ void __launch_bounds__(NT)
+perm_walk_binary_pm(const __grid_constant__ WalkParamsM<NC> Q)
+{
+    binary_walk_body<NC, B, NT>(Q.P, Q.m);
+}
+
+#ifdef PQ_BINARY_CONST_MATRIX
+template <int NC, int B, int NT>
+__global__ void __launch_bounds__(NT) perm_walk_binary(const __grid_constant__ WalkParams P)
+{
+    binary_walk_body<NC, B, NT>(P, PQ_BINARY_CONST_MATRIX);
 }
 #endif // PQ_BINARY_CONST_MATRIX
 
