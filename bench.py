@@ -26,6 +26,10 @@ work is fixed).  Rank 0 prints ONE JSON line.
   throughput measured in this run (MEASURED_PEAKS.json has no FP64 entry).
 * ``cpu_baseline`` (N=1) -- the reference's own C++ (oracle/_ref) on this
   box's host cores, on a bounded sample of the same workload.
+* ``secondary`` -- BASELINE configs[0..3] measured in the same run
+  (bench_secondary.py): n=20 / n=30 permanents and the 60-mode n-ary cases with
+  the reference timed on the SAME input (N=1), and the 10^4-shot sampler, whose
+  shots are sharded over the ranks at N>1.
 """
 
 from __future__ import annotations
@@ -49,11 +53,27 @@ import numpy as np  # noqa: E402
 METRIC = "n40_c128_permanent_gray_code_terms_per_s"
 UNIT = "terms/s"
 NOMINAL_FP64_TFLOPS = 37.2  # 148 SM x 64 lanes x 2 flop x 1.965 GHz
-# dram__bytes_read.sum + dram__bytes_write.sum of the walk kernel, from the
-# `ncu --set full` capture summarised in profiles/r01_ncu_summary.md (n=30
-# launch: 61.4 KB read, 0 written; the n=40 launch stages the same kind of
-# <= 26 KB matrix once per CTA out of L2).  Algorithmic bytes are n^2*16 + 32.
-TRAFFIC_BYTES_PER_LAUNCH = 61440
+# `ncu --set full` capture of the headline instantiation (committed under profiles/):
+# roofline.traffic is read from it, never typed in.
+TRAFFIC_NCU_CSV = os.path.join(ROOT, "profiles", "r02_ncu_perm_walk_binary_n40_raw.csv")
+
+
+def traffic_from_ncu(path=TRAFFIC_NCU_CSV):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes, one launch) of the
+    walk kernel from the committed ncu raw-page CSV; None when it is absent."""
+    import csv
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        with open(path, newline="") as fh:
+            rows = list(csv.reader(fh))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        total = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            total += float(vals[i].replace(",", "")) * scale[units[i]]
+        return total
+    except (OSError, ValueError, IndexError, KeyError):
+        return None
 
 
 def haar_matrix(n, seed):
@@ -237,9 +257,13 @@ def main_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION/INFO print there)
-        if not os.environ.get("PQ_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL's own log is the evidence of the communicator (ranks, transport): keep
+        # it visible.  Whatever the launcher set is left alone; otherwise the INIT
+        # lines go to stderr, so that stdout stays the one JSON line.
+        if "NCCL_DEBUG" not in os.environ:
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -327,6 +351,17 @@ def main_arm(args):
     h2d = int((info.active_rows + 1) * info.cols_padded * 16) * world
     d2h = 32 * world
 
+    # ---- the other BASELINE configs, same run (all ranks: the sampler is sharded) ----
+    secondary = None
+    if not args.no_secondary:
+        import bench_secondary
+        t0 = time.perf_counter()
+        secondary = bench_secondary.run(lib, peak, rank, world, local_rank,
+                                        with_reference=(world == 1 and rank == 0),
+                                        sampler_shots=args.sampler_shots)
+        if secondary is not None:
+            secondary["seconds_spent"] = time.perf_counter() - t0
+
     line = None
     if rank == 0:
         ms_per_step = elapsed_ms / K
@@ -350,7 +385,10 @@ def main_arm(args):
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak > 0 else None,
-                "traffic": TRAFFIC_BYTES_PER_LAUNCH,
+                "traffic": traffic_from_ncu(),
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                  "perm_walk_binary_pm<40,3,64> launch, ncu --set full, "
+                                  "profiles/" + os.path.basename(TRAFFIC_NCU_CSV),
                 "peak_source": "measured in this run on rank 0's GPU: dependent-free DFMA loop, "
                                "2 flop per FMA (pq_fp64_peak_tflops); MEASURED_PEAKS.json holds "
                                "no FP64 figure",
@@ -377,11 +415,14 @@ def main_arm(args):
                                     "seconds": cb["seconds_per_step"]}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        line["secondary"] = secondary
     lib.pq_perm_job_destroy(job)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if line is not None:
+        # printed last, after NCCL has said everything it had to say
+        print(json.dumps(line), flush=True)
     return 0
 
 
@@ -395,6 +436,10 @@ def main():
     ap.add_argument("--seed", type=int, default=40)
     ap.add_argument("--ref-digits", type=int, default=25,
                     help="binary Gray digits of the reference's bounded sample")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the other BASELINE configs (the `secondary` object)")
+    ap.add_argument("--sampler-shots", type=int, default=10000,
+                    help="shots of the configs[3] sampler run in `secondary`")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

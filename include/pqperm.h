@@ -41,8 +41,8 @@ extern "C" {
  * for the partitioned entries (pq_perm_partial_c128, pq_perm_job_*, pq_perm_plan);
  * <= PQ_MAX_COLS_WIDE for pq_perm_c128 / pq_perm_c64 / pq_perm_batch_c128, the
  * permanent_laplace entries and the sampler steps -- beyond PQ_MAX_COLS a whole
- * warp walks each Gray segment, and (active rows + 1) x columns x 16 bytes must
- * fit in 200 KB of shared memory. */
+ * warp walks each Gray segment, and (active rows + 1) x columns x 16 bytes plus
+ * 36 KB of accumulators must fit in 224 KB of shared memory. */
 #define PQ_MAX_COLS 64
 #define PQ_MAX_COLS_WIDE 256
 #define PQ_MAX_DIGITS 64
@@ -164,6 +164,8 @@ int pq_sampler_draw_c128(const double *U, int d, int nshots, const int32_t *out_
 int pq_sampler_draw_dev_c128(int device, const double *U, int d, int nshots,
                              const int32_t *out_occ, const int32_t *in_occ, const double *u,
                              int32_t *index);
+int pq_sampler_pmf_dev_c128(int device, const double *U, int d, int nshots,
+                            const int32_t *out_occ, const int32_t *in_occ, double *pmf);
 
 /* Where the calling thread's last pq_sampler_* call spent its wall time, in
  * milliseconds: out_ms[0] planning on the host (zero filtering, problem
@@ -171,6 +173,18 @@ int pq_sampler_draw_dev_c128(int device, const double *U, int d, int nshots,
  * kernels, download, scatter), [3] the kernels alone (CUDA events).  Diagnostic
  * only; the reference has no counterpart. */
 void pq_last_sampler_profile(double out_ms[4]);
+
+/* Finer split of the device phase of the calling thread's last pq_sampler_* call
+ * (ms): [0] scratch growth, [1] staging descriptors into pinned memory, [2]
+ * enqueueing copies and launches, [3] waiting for the stream, [4] scattering the
+ * results, [5] uploading the interferometer; [6..7] reserved.  Diagnostic only. */
+void pq_last_sampler_detail(double out_ms[8]);
+
+/* Work done by all pq_sampler_* steps of this process since the last reset:
+ * out[0] = Gray-code terms walked, out[1] = algorithmic flops (22 k per term of
+ * a k-column Laplace problem).  For roofline reports. */
+void pq_sampler_work(double out[2]);
+void pq_sampler_work_reset(void);
 
 /* ---------------------------------------------------------------------
  * Partitioned permanent: the piece of one permanent that rank `part` of
@@ -185,6 +199,12 @@ void pq_last_sampler_profile(double out_ms[4]);
  * synchronised before returning).  The caller gathers the four doubles of
  * every rank (one NCCL all-gather), sums them with pq_perm_combine and calls
  * pq_perm_finish.
+ *
+ * The walk kernels of one device share scratch memory (the staged matrix, the
+ * per-CTA partials, the segment dispenser).  The library orders its own use of
+ * that scratch on the device: a launch that follows one enqueued on a DIFFERENT
+ * stream first waits for it (cudaStreamWaitEvent), so callers need not
+ * synchronise their stream before the next library call.
  *
  * *status (host int, may be NULL) receives 0 when a partial was enqueued or
  * 1 when the problem is one of the reference's trivial cases and `trivial`

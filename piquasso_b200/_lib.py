@@ -75,6 +75,8 @@ SIGNATURES = [
     ("pq_sampler_draw_dev_c128", ctypes.c_int,
      [ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, c_double_p,
       c_int32_p]),
+    ("pq_sampler_pmf_dev_c128", ctypes.c_int,
+     [ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, c_double_p]),
     ("pq_perm_partial_c128", ctypes.c_int,
      [c_double_p, ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, ctypes.c_int,
       ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
@@ -101,6 +103,9 @@ SIGNATURES = [
     ("pq_launch_count", ctypes.c_int64, []),
     ("pq_perm_arbiter_c128", ctypes.c_int, [c_double_p, ctypes.c_int, ctypes.c_int, c_int32_p,
                                             c_int32_p, c_double_p]),
+    ("pq_last_sampler_detail", None, [c_double_p]),
+    ("pq_sampler_work", None, [c_double_p]),
+    ("pq_sampler_work_reset", None, []),
     ("pq_fp64_peak_tflops", ctypes.c_double, [ctypes.c_int, ctypes.c_int]),
     ("pq_set_kernel_choice", ctypes.c_int, [ctypes.c_int]),
     ("pq_set_seg_len_hint", ctypes.c_int, [ctypes.c_int64]),

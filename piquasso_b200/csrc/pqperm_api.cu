@@ -143,6 +143,8 @@ int grow_dev(DeviceCtx *c, int slot, size_t bytes)
         return PQ_OK;
     if (c->d_lap[slot])
         cudaFree(c->d_lap[slot]);
+    if (slot == 4)
+        c->u_host.clear(); // the resident interferometer goes with its buffer
     c->d_lap[slot] = nullptr;
     c->d_lap_cap[slot] = 0;
     const size_t cap = bytes + bytes / 2 + 4096;
@@ -382,6 +384,7 @@ extern "C" double pq_last_kernel_ms(int device)
     std::lock_guard<std::mutex> lock(g_mu);
     if (device < 0 || device >= (int)g_ctx.size() || !g_ctx[device])
         return -1.0;
+    std::lock_guard<std::mutex> dev_lock(g_ctx[device]->mu);
     return g_ctx[device]->last_kernel_ms;
 }
 
@@ -533,6 +536,11 @@ static int perm_run(const double *A, int R, int C, const int32_t *rows, const in
     }
     // small problems are not worth a second device
     const int used = (ndev > 1 && plan.nseg >= (int64_t)ndev * 4096) ? std::min(ndev, 64) : 1;
+    // device phase: under the per-device locks (lock order: g_mu, then devices)
+    std::vector<std::unique_lock<std::mutex>> dev_locks;
+    dev_locks.reserve(used);
+    for (int i = 0; i < used; i++)
+        dev_locks.emplace_back(ctx[i]->mu);
     for (int i = 0; i < used; i++) {
         DeviceCtx *c = ctx[i];
         if (ndev > 1)
@@ -622,6 +630,7 @@ extern "C" int pq_perm_partial_c128(const double *A, int R, int C, const int32_t
     int64_t b, e;
     split_range(plan.nseg, part, nparts, &b, &e);
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    std::lock_guard<std::mutex> dev_lock(c->mu);
     if (b < e) {
         rc = enqueue_walk(plan, c, b, e, d_partial, nullptr, s);
         if (rc)
@@ -660,6 +669,7 @@ extern "C" int pq_perm_segment_sums_c128(const double *A, int R, int C, const in
         return fail(PQ_ERR_BAD_ARG, "trivial problem has no segments");
     if (seg_begin + nseg > plan.nseg)
         return fail(PQ_ERR_BAD_ARG, "segment range outside the plan");
+    std::lock_guard<std::mutex> dev_lock(c->mu);
     double *d_seg = nullptr;
     PQ_CUDA(cudaMalloc(&d_seg, (size_t)nseg * 2 * sizeof(double)));
     PQ_CUDA(cudaMemsetAsync(d_seg, 0, (size_t)nseg * 2 * sizeof(double), c->stream));
@@ -682,6 +692,7 @@ extern "C" double pq_fp64_peak_tflops(int device, int iters)
     DeviceCtx *c = nullptr;
     if (ctx_get(device, &c))
         return -1.0;
+    std::lock_guard<std::mutex> dev_lock(c->mu);
     if (iters < 1)
         iters = 1 << 16;
     double best = -1.0;
@@ -749,6 +760,7 @@ extern "C" int pq_perm_job_create_c128(const double *A, int R, int C, const int3
         if (rc)
             return fail(rc, err);
     }
+    std::lock_guard<std::mutex> dev_lock(c->mu);
     j->id = g_job_ids++;
     j->device = device;
     split_range(j->plan.nseg, part, nparts, &j->seg_begin, &j->seg_end);
@@ -775,6 +787,7 @@ extern "C" int pq_perm_job_launch(pq_perm_job *job, void *stream, double *d_part
     if (rc)
         return rc;
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    std::lock_guard<std::mutex> dev_lock(c->mu);
     if (!rides_in_params(job->plan) && c->resident_job != job->id) {
         // evicted by another call on this device
         rc = upload_plan(job->plan, c, s);
@@ -827,6 +840,7 @@ extern "C" int pq_kernel_ms_history(int device, double *out, int max)
     if (device < 0 || device >= (int)g_ctx.size() || !g_ctx[device] || !out || max < 1)
         return 0;
     DeviceCtx *c = g_ctx[device].get();
+    std::lock_guard<std::mutex> dev_lock(c->mu);
     int n = 0;
     for (uint64_t k = c->ring_next; k > 0 && n < max && n < kTimingRing; k--) {
         const int slot = (int)((k - 1) % kTimingRing);

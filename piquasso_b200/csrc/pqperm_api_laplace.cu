@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -35,6 +36,20 @@ constexpr long long kLapBigProblem = 1LL << 18;       // terms
 constexpr int kPlanThreadsMax = 8;
 // ... as long as every thread gets at least this many shots
 constexpr int kPlanShotsPerThread = 1024;
+
+// Finer split of the device phase of the calling thread's last sampler step (ms):
+// [0] scratch growth, [1] staging into pinned memory, [2] enqueueing (copies,
+// launches), [3] waiting for the stream, [4] scattering results, [5] uploading U.
+thread_local double g_sampler_detail[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+struct Lap {
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void to(double &slot)
+    {
+        const auto now = std::chrono::steady_clock::now();
+        slot += std::chrono::duration<double, std::milli>(now - t).count();
+        t = now;
+    }
+};
 
 // What the lean planner extracts from one problem's multiplicity vectors
 // (zeros allowed).  Restates src/permanent_laplace.cpp:49-118 of the reference
@@ -228,6 +243,7 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
     }
     const size_t out_bytes = (size_t)n * ncp1 * sizeof(double2);
     int rc;
+    Lap lap;
     if ((rc = grow_dev(c, 0, sizeof(LapProblem) * (size_t)n)) ||
         (rc = grow_dev(c, 2, (size_t)total_blocks * ncp1 * 4 * sizeof(double))) ||
         (rc = grow_dev(c, 3, out_bytes)))
@@ -238,7 +254,9 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
     // host's pages (megabytes per photon step in the sampler)
     if ((rc = grow_host(c, 4, sizeof(LapProblem) * (size_t)n)))
         return rc;
+    lap.to(g_sampler_detail[0]);
     std::memcpy(c->h_lap[4], bk.probs.data(), sizeof(LapProblem) * (size_t)n);
+    lap.to(g_sampler_detail[1]);
     PQ_CUDA(cudaMemcpyAsync(c->d_lap[0], c->h_lap[4], sizeof(LapProblem) * (size_t)n,
                             cudaMemcpyHostToDevice, st));
     LapParams P;
@@ -321,7 +339,9 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
     }
     PQ_CUDA(cudaEventRecord(c->lap_ev1, st));
     PQ_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    lap.to(g_sampler_detail[2]);
     PQ_CUDA(cudaStreamSynchronize(st));
+    lap.to(g_sampler_detail[3]);
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->lap_ev0, c->lap_ev1) == cudaSuccess)
         c->last_kernel_ms = (c->last_kernel_ms < 0 ? 0.0 : c->last_kernel_ms) + ms;
@@ -335,6 +355,7 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
             std::memcpy(epi->pmf + (size_t)bk.probs[i].tag * epi->ldu, src + (size_t)i * epi->ldu,
                         (size_t)epi->ldu * sizeof(double));
     }
+    lap.to(g_sampler_detail[4]);
     return PQ_OK;
 }
 
@@ -352,6 +373,8 @@ int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const
     for (int b = 0; b < nprob; b++) {
         if (R[b] < 0 || C[b] < 0)
             return fail(PQ_ERR_BAD_ARG, "negative shape in batch");
+        if ((R[b] > 0 && !rows) || (C[b] > 0 && !cols) || (R[b] > 0 && C[b] > 0 && !A))
+            return fail(PQ_ERR_BAD_ARG, "null matrix or multiplicity vector in batch");
         const int32_t *rw = rows + r_off[b], *cl = cols + c_off[b];
         const int rc = lap_shape(R[b], C[b], rw, cl, sh, err);
         if (rc)
@@ -444,6 +467,18 @@ int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const
 // planning, waiting for the device lock, device phase (uploads, kernels,
 // download, scatter), and the kernels alone (CUDA events).
 thread_local double g_sampler_profile[4] = {0.0, 0.0, 0.0, 0.0};
+// Gray-code terms and algorithmic flops (22 k per term of a k-column problem,
+// SURVEY.md 8d) of all sampler steps since the last reset, over all threads
+std::atomic<double> g_sampler_terms{0.0}, g_sampler_flops{0.0};
+void add_work(double terms, double flops)
+{
+    double cur = g_sampler_terms.load();
+    while (!g_sampler_terms.compare_exchange_weak(cur, cur + terms)) {
+    }
+    cur = g_sampler_flops.load();
+    while (!g_sampler_flops.compare_exchange_weak(cur, cur + flops)) {
+    }
+}
 
 // numpy's Generator.choice(d, p = row / sum(row)) for the uniform variate u, on
 // the host (shots whose Laplace problem is the reference's early-out)
@@ -608,6 +643,16 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
         }
     }
     g_sampler_profile[0] = ms_since(t_begin);
+    {
+        double terms = 0.0, flops = 0.0;
+        for (const Bucket &bk : g_buckets.b)
+            for (const LapProblem &q : bk.probs) {
+                const double t = (double)q.nseg * (double)q.W;
+                terms += t;
+                flops += t * 22.0 * (double)q.nc;
+            }
+        add_work(terms, flops);
+    }
     if (!any) {
         // nothing to launch (e.g. the first photon of every shot): no kernel time
         std::lock_guard<std::mutex> lock(g_mu);
@@ -629,10 +674,48 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
     std::lock_guard<std::mutex> dev_lock(c->mu);
     g_sampler_profile[1] = ms_since(t_planned);
     const auto t_locked = std::chrono::steady_clock::now();
+    for (double &x : g_sampler_detail)
+        x = 0.0;
+    Lap lap;
     const size_t ubytes = (size_t)d * d * sizeof(double2);
     if ((rc = grow_dev(c, 4, ubytes)))
         return rc;
-    PQ_CUDA(cudaMemcpyAsync(c->d_lap[4], U, ubytes, cudaMemcpyHostToDevice, c->stream));
+    {
+        // Size the scratch ONCE for this many shots: the photon steps of a run come
+        // with growing column counts, and regrowing pinned / device buffers step
+        // after step (free + allocate, megabytes each) is what the device phase was
+        // losing milliseconds to.  Bounds: NCP + 1 <= min(d, 64) + 1 columns per
+        // result, at most 4 waves + one CTA per shot.
+        const size_t ns = (size_t)nshots;
+        const size_t ncp1_max = (size_t)std::min(d, (int)kMaxCols) + 1;
+        const size_t blocks_max = (size_t)4 * c->num_sms * 8 + ns;
+        if ((rc = grow_dev(c, 0, sizeof(LapProblem) * ns)) ||
+            (rc = grow_host(c, 4, sizeof(LapProblem) * ns)) ||
+            (rc = grow_dev(c, 2, blocks_max * ncp1_max * 4 * sizeof(double))) ||
+            (rc = grow_dev(c, 3, ns * ncp1_max * sizeof(double2))) ||
+            (rc = grow_dev(c, 5, ns * (size_t)d * sizeof(double))))
+            return rc;
+        if (pmf) {
+            if ((rc = grow_host(c, 3, ns * (size_t)d * sizeof(double))))
+                return rc;
+        } else if ((rc = grow_dev(c, 6, ns * sizeof(double))) ||
+                   (rc = grow_dev(c, 7, ns * sizeof(int32_t))) ||
+                   (rc = grow_host(c, 0, ns * sizeof(double))) ||
+                   (rc = grow_host(c, 1, ns * sizeof(int32_t)))) {
+            return rc;
+        }
+    }
+    lap.to(g_sampler_detail[0]);
+    // the interferometer changes only between runs: upload it when it differs from
+    // the resident copy (compared on the host, 16 d^2 bytes)
+    if (c->u_host.size() != ubytes / sizeof(double) ||
+        std::memcmp(c->u_host.data(), U, ubytes) != 0) {
+        c->u_host.assign(U, U + ubytes / sizeof(double));
+        PQ_CUDA(cudaMemcpyAsync(c->d_lap[4], c->u_host.data(), ubytes, cudaMemcpyHostToDevice,
+                                c->stream));
+        PQ_CUDA(cudaStreamSynchronize(c->stream)); // u_host is pageable: settle it now
+    }
+    lap.to(g_sampler_detail[5]);
     Epilogue epi;
     epi.d_U = reinterpret_cast<const double2 *>(c->d_lap[4]);
     epi.ldu = d;
@@ -709,6 +792,7 @@ int perm_batch_locked(const double *U, int R, int C, int nprob, const int32_t *r
     const size_t ubytes = (size_t)R * C * sizeof(double2);
     if ((rc = grow_dev(c, 4, ubytes)))
         return rc;
+    c->u_host.clear(); // the sampler's resident interferometer is overwritten
     PQ_CUDA(cudaMemcpyAsync(c->d_lap[4], U, ubytes, cudaMemcpyHostToDevice, c->stream));
     Epilogue epi;
     epi.d_U = reinterpret_cast<const double2 *>(c->d_lap[4]);
@@ -766,6 +850,18 @@ extern "C" int pq_sampler_pmf_c128(const double *U, int d, int nshots, const int
     return sampler_step(U, d, nshots, out_occ, in_occ, pmf);
 }
 
+extern "C" int pq_sampler_pmf_dev_c128(int device, const double *U, int d, int nshots,
+                                       const int32_t *out_occ, const int32_t *in_occ,
+                                       double *pmf)
+{
+    if (device < 0 || d < 1 || d > 65535 || nshots < 0 || !U ||
+        (nshots > 0 && (!out_occ || !in_occ || !pmf)))
+        return fail(PQ_ERR_BAD_ARG, "bad sampler arguments");
+    if (nshots == 0)
+        return PQ_OK;
+    return sampler_step(U, d, nshots, out_occ, in_occ, pmf, nullptr, nullptr, device);
+}
+
 extern "C" int pq_sampler_draw_c128(const double *U, int d, int nshots, const int32_t *out_occ,
                                     const int32_t *in_occ, const double *u, int32_t *index)
 {
@@ -775,6 +871,24 @@ extern "C" int pq_sampler_draw_c128(const double *U, int d, int nshots, const in
     if (nshots == 0)
         return PQ_OK;
     return sampler_step(U, d, nshots, out_occ, in_occ, nullptr, u, index);
+}
+
+extern "C" void pq_last_sampler_detail(double out_ms[8])
+{
+    for (int i = 0; i < 8; i++)
+        out_ms[i] = g_sampler_detail[i];
+}
+
+extern "C" void pq_sampler_work(double out[2])
+{
+    out[0] = g_sampler_terms.load();
+    out[1] = g_sampler_flops.load();
+}
+
+extern "C" void pq_sampler_work_reset(void)
+{
+    g_sampler_terms.store(0.0);
+    g_sampler_flops.store(0.0);
 }
 
 extern "C" void pq_last_sampler_profile(double out_ms[4])

@@ -353,6 +353,8 @@ extern "C" int pq_perm_arbiter_c128(const double *A, int R, int C, const int32_t
         (rc = grow_host(c, 2, (size_t)grid * 4 * sizeof(double))))
         return rc;
     cudaStream_t st = c->stream;
+    if (c->busy_valid) // a walk on a caller's stream may still be drawing from the dispenser
+        PQ_CUDA(cudaStreamWaitEvent(st, c->ev_busy, 0));
     PQ_CUDA(cudaMemcpyAsync(c->d_lap[1], plan.A2.data(), a2_bytes, cudaMemcpyHostToDevice, st));
     PQ_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
     P.A2 = reinterpret_cast<const double2 *>(c->d_lap[1]);
@@ -364,6 +366,8 @@ extern "C" int pq_perm_arbiter_c128(const double *A, int R, int C, const int32_t
         return fail_cuda(e, "launch arbiter_kernel");
     g_launches += 1;
     PQ_CUDA(cudaEventRecord(c->lap_ev1, st));
+    // the walk kernels expect their dispenser at zero between launches
+    PQ_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
     PQ_CUDA(cudaMemcpyAsync(c->h_lap[2], c->d_lap[2], (size_t)grid * 4 * sizeof(double),
                             cudaMemcpyDeviceToHost, st));
     PQ_CUDA(cudaStreamSynchronize(st));

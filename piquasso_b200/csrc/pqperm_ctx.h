@@ -51,9 +51,13 @@ struct DeviceCtx {
     uint64_t resident_job = 0;     // id of the pq_perm_job whose inputs sit in the blob
     cudaEvent_t ring0[kTimingRing], ring1[kTimingRing];  // event pairs around the kernels
     uint64_t ring_next = 0;
-    // The batched Laplace / sampler path: its device phase runs under `mu` (not
-    // under the library-wide g_mu), so that host threads driving DIFFERENT devices
-    // overlap; it touches only the members below plus `stream`.
+    // ONE lock story: `mu` guards everything of this context that a device phase
+    // touches -- `stream`, the scratch above and below, the timers.  Every entry
+    // point takes it for its device phase.  g_mu (library-wide) only guards the
+    // global tables and settings; the permanent entries additionally keep it for the
+    // whole call (one permanent at a time), the sampler steps release it before their
+    // device phase so that host threads driving DIFFERENT devices overlap.  Lock
+    // order: g_mu, then device locks in the order of the device list.
     std::mutex mu;
     cudaEvent_t lap_ev0 = nullptr, lap_ev1 = nullptr;
     // growable scratch of the batched Laplace path
@@ -61,6 +65,7 @@ struct DeviceCtx {
     void *d_lap[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                       nullptr};
     size_t d_lap_cap[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<double> u_host;  // host copy of the matrix resident in d_lap[4] (sampler)
     // (pinned) uniform draws, drawn indices, out, pmf, problem descriptors
     void *h_lap[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t h_lap_cap[5] = {0, 0, 0, 0, 0};

@@ -50,7 +50,7 @@ cudaError_t launch_laplace_general(
     PQ_CASE(1, 7) PQ_CASE(1, 8)
     PQ_CASE(2, 5) PQ_CASE(2, 6) PQ_CASE(2, 7) PQ_CASE(2, 8) PQ_CASE(2, 9) PQ_CASE(2, 10) PQ_CASE(2, 11) PQ_CASE(2, 12)
     PQ_CASE(2, 13)
-    PQ_CASE(4, 7) PQ_CASE(4, 8) PQ_CASE(4, 9) PQ_CASE(4, 10) PQ_CASE(4, 11) PQ_CASE(4, 12)
+    PQ_CASE(4, 5) PQ_CASE(4, 6) PQ_CASE(4, 7) PQ_CASE(4, 8) PQ_CASE(4, 9) PQ_CASE(4, 10) PQ_CASE(4, 11) PQ_CASE(4, 12)
     PQ_CASE(4, 13) PQ_CASE(4, 14) PQ_CASE(4, 15) PQ_CASE(4, 16)
     PQ_CASE(32, 3) PQ_CASE(32, 4) PQ_CASE(32, 5) PQ_CASE(32, 6) PQ_CASE(32, 7) PQ_CASE(32, 8)
 #undef PQ_CASE

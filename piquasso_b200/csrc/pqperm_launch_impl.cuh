@@ -25,12 +25,15 @@ struct OccKey {
 };
 
 // Resident blocks per SM for (kernel, smem) on the current device, cached; also
-// raises the dynamic shared memory limit the first time it is needed.
+// raises the kernel's dynamic shared memory limit when needed -- only ever RAISES
+// it (a later, smaller request above 48 KB must not lower the limit a cached,
+// larger configuration relies on).
 template <typename KernelT>
 inline cudaError_t resident_blocks(KernelT kernel, int NT, size_t smem, int *nb)
 {
     static std::mutex mu;
     static std::map<OccKey, int> cache;
+    static std::map<std::pair<const void *, int>, size_t> raised; // (kernel, device) -> limit
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess)
@@ -43,10 +46,14 @@ inline cudaError_t resident_blocks(KernelT kernel, int NT, size_t smem, int *nb)
         return cudaSuccess;
     }
     if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem);
-        if (e != cudaSuccess)
-            return e;
+        size_t &limit = raised[std::make_pair((const void *)kernel, dev)];
+        if (limit < smem) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem);
+            if (e != cudaSuccess)
+                return e;
+            limit = smem;
+        }
     }
     int n = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, NT, smem);

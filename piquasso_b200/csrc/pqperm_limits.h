@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cstdint>
+#include <cstdlib>
 
 namespace pqperm {
 
@@ -17,10 +18,10 @@ constexpr int kBinMaxBlockExp = 4;      // kernel 2: at most 2^4 terms per block
 // kernel 2: log2 of the terms per block for nc columns (register budget:
 // 4*nc for the row sums + 4 * 2^B for the running products)
 inline int binary_block_exponent(int /*nc*/) { return 3; }  // measured best for 20 <= nc <= 48
-// Below 2^kBinMinDigitsAuto terms the generic walk is used.  (Was 25 while the
-// binary walk needed its matrix uploaded into a __constant__ array first; with the
-// matrix riding in the kernel parameters its setup cost is that of any launch.)
-constexpr int kBinMinDigitsAuto = 12;
+// Below 2^kBinMinDigitsAuto terms the generic walk is used (measured on B200,
+// tools/r2_probe.py: n = 24 generic 127 us / binary 145 us, n = 26 generic 502 us /
+// binary 412 us).
+constexpr int kBinMinDigitsAuto = 25;
 constexpr int64_t kMaxSegLenBinary = INT64_C(1) << 14;
 constexpr int64_t kMaxSegLenNary = INT64_C(1) << 10;  // step tables live in shared memory (9 KB)
 
@@ -42,11 +43,20 @@ struct LapVariant {
     int S;
     int NCL;
 };
+// experiments: PQ_LAP_S4_FROM=n uses four lanes per segment from n columns on
+inline int lap_s4_from()
+{
+    static const int v = [] {
+        const char *e = std::getenv("PQ_LAP_S4_FROM");
+        return e ? std::atoi(e) : 27;
+    }();
+    return v < 17 ? 17 : v;
+}
 inline LapVariant laplace_variant(int nc)
 {
     if (nc <= 8)
         return {1, nc < 1 ? 1 : nc};
-    if (nc <= 26)
+    if (nc <= 26 && nc < lap_s4_from())
         return {2, (nc + 1) / 2};
     if (nc <= kMaxCols)
         return {4, (nc + 3) / 4};

@@ -157,12 +157,22 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
 
     // ---- where to cut the digits --------------------------------------------
     // cost(q) ~ waves(q) * (seed + W(q) * step); see DESIGN.md "partition".
-    // registers per thread: the binary walk's are known (ptxas, 64-thread CTAs)
-    const double regs = plan.kernel == 2
-                            ? (plan.NC <= 16 ? 128.0 : (plan.NC <= 26 ? 168.0 : 255.0))
-                            : 4.0 * plan.NCP + 48.0;
-    double resident = std::floor(65536.0 / regs / 64.0) * 64.0;
-    resident = std::max(64.0, std::min(2048.0, resident)) * opt.num_sms;
+    // Threads resident on the device: registers per thread as ptxas reports them
+    // (profiles/r02_ptxas_v.txt), CTA sizes as the launchers use them.
+    double regs, nt;
+    if (plan.kernel == 2) {
+        nt = 64.0;
+        regs = plan.NC <= 16 ? 128.0 : (plan.NC <= 26 ? 168.0 : 255.0);
+    } else {
+        nt = plan.NCP <= 16 ? 128.0 : 64.0;
+        regs = plan.NCP <= 4 ? 68.0
+               : plan.NCP <= 8 ? 102.0
+               : plan.NCP <= 16 ? 128.0
+               : plan.NCP <= 24 ? 168.0
+               : (plan.NCP <= 28 && plan.unitcols) ? 168.0 : 255.0;
+    }
+    const double ctas = std::max(1.0, std::min(32.0, std::floor(65536.0 / (nt * regs))));
+    const double resident = std::min(2048.0, ctas * nt) * opt.num_sms;
     const double step = 2.0 * plan.NCP + 4.0 * plan.M + 2.0;
     const double seed = 2.0 * plan.NCP * (plan.D + 1) + 40.0 * plan.D + 100.0;
     const int64_t wmax = (plan.binary && plan.unitcols) ? kMaxSegLenBinary : kMaxSegLenNary;
@@ -184,6 +194,8 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
                     best_q = q;
                 continue;
             }
+            // a partly filled last wave costs a whole one: the dispenser hands out
+            // 32 segments per warp and every warp ends up with ceil(.) batches
             const double nseg = (double)(plan.idx_max / W);
             const double waves = std::ceil(nseg / resident);
             const double cost = waves * (seed + (double)W * step);

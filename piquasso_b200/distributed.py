@@ -154,7 +154,8 @@ def permanent_laplace_allgather(matrix, rows, cols, group=None, device_index=Non
 
 
 def generate_samples_sharded(input, shots, interferometer, seed_sequence,
-                             reject_condition=None, group=None, pmf_rows=None):
+                             reject_condition=None, group=None, pmf_rows=None,
+                             device_index=None):
     """The lock-step sampler with the SHOTS sharded over the ranks of ``group``.
 
     Shots are independent (shot ``idx`` owns ``default_rng(seed_sequence + idx)``),
@@ -162,6 +163,10 @@ def generate_samples_sharded(input, shots, interferometer, seed_sequence,
     GPU; there is no exchange step on the data path, only one all-gather of the
     finished samples at the end.  Every rank returns the full list, identical to
     the single-GPU (and to the reference's) result.
+
+    ``device_index`` is the CUDA device this rank's shots run on; the default is
+    the rank's current torch device (``torch.cuda.current_device()``), i.e. what
+    ``torch.cuda.set_device(LOCAL_RANK)`` selected -- never silently device 0.
 
     ``reject_condition`` is evaluated by every rank for ALL shots in the
     reference's shot-major order (it may draw from a generator the ranks seeded
@@ -182,14 +187,17 @@ def generate_samples_sharded(input, shots, interferometer, seed_sequence,
         table = [[bool(reject_condition()) for _ in range(n)] for _ in range(shots)]
         flat = iter([x for row in table[begin:end] for x in row])
         rejects = lambda: next(flat)  # noqa: E731
+    devices = None
+    if pmf_rows is None:
+        if device_index is None:
+            import torch
+            device_index = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        devices = [int(device_index)]
     mine = generate_samples(input, end - begin, interferometer, seed_sequence + begin,
-                            reject_condition=rejects, pmf_rows=pmf_rows)
+                            reject_condition=rejects, pmf_rows=pmf_rows, devices=devices)
     if world == 1:
         return mine
     gathered = [None] * world
     dist.all_gather_object(gathered, mine, group=group)
     return [s for part in gathered for s in part]
 
-
-# the exchange step used to be an all-reduce; keep the old name importable
-permanent_allreduce = permanent_allgather

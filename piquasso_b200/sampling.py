@@ -173,11 +173,12 @@ def _to_first_quantized(occupation):
     return np.array(out, dtype=int)
 
 
-def sampler_pmf(interferometer, out_occ, in_occ):
+def sampler_pmf(interferometer, out_occ, in_occ, device=None):
     """Unnormalised pmf rows of one photon step for many shots at once
     (``pq_sampler_pmf_c128``): row s is ``_calculate_pmf(in_occ[s], out_occ[s],
     permanent_laplace, interferometer)`` of the reference before normalisation
-    (``piquasso/_simulators/passive/sampling.py:723-749``)."""
+    (``piquasso/_simulators/passive/sampling.py:723-749``).  ``device`` selects a
+    CUDA device explicitly (``pq_sampler_pmf_dev_c128``)."""
     lib = _lib.load()
     U = np.ascontiguousarray(interferometer, dtype=np.complex128)
     d = U.shape[0]
@@ -188,16 +189,19 @@ def sampler_pmf(interferometer, out_occ, in_occ):
     if oo.shape != io.shape:
         raise ValueError("out_occ and in_occ must have the same shape")
     pmf = np.empty(oo.shape, dtype=np.float64)
-    rc = lib.pq_sampler_pmf_c128(
-        U.ctypes.data_as(_lib.c_double_p), d, oo.shape[0],
-        oo.ctypes.data_as(_lib.c_int32_p), io.ctypes.data_as(_lib.c_int32_p),
-        pmf.ctypes.data_as(_lib.c_double_p))
+    args = (U.ctypes.data_as(_lib.c_double_p), d, oo.shape[0],
+            oo.ctypes.data_as(_lib.c_int32_p), io.ctypes.data_as(_lib.c_int32_p),
+            pmf.ctypes.data_as(_lib.c_double_p))
+    if device is None:
+        rc = lib.pq_sampler_pmf_c128(*args)
+    else:
+        rc = lib.pq_sampler_pmf_dev_c128(int(device), *args)
     if rc in (_lib.PQ_ERR_BAD_ARG, _lib.PQ_ERR_TOO_LARGE):
         raise ValueError(_lib.last_error())
     _lib.check(rc)
     TIMERS["  of which GPU kernels (CUDA events)"] = (
         TIMERS.get("  of which GPU kernels (CUDA events)", 0.0)
-        + max(lib.pq_last_kernel_ms(0), 0.0) * 1e-3)
+        + max(lib.pq_last_kernel_ms(0 if device is None else int(device)), 0.0) * 1e-3)
     return pmf
 
 
@@ -237,6 +241,13 @@ def sampler_draw(interferometer, out_occ, in_occ, uniforms, device=None):
     lib.pq_last_sampler_profile(prof)
     for name, ms in zip(("  of which planning (host threads)", "  of which waiting for the device",
                          "  of which device phase", "  of which GPU kernels (CUDA events)"), prof):
+        TIMERS[name] = TIMERS.get(name, 0.0) + ms * 1e-3
+    detail = (ctypes.c_double * 8)()
+    lib.pq_last_sampler_detail(detail)
+    for name, ms in zip(("    device phase: scratch growth", "    device phase: staging descriptors",
+                         "    device phase: enqueue", "    device phase: waiting for the stream",
+                         "    device phase: scatter", "    device phase: interferometer upload"),
+                        detail):
         TIMERS[name] = TIMERS.get(name, 0.0) + ms * 1e-3
     return index
 
@@ -345,10 +356,17 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
 
     if ((postselect_data is not None and len(postselect_data[0]) > 0)
             or uniform_particle_overlap is not None):
+        if pmf_rows is None:
+            # the coroutine engine issues one batched call per round: it runs on the
+            # first of `devices` (shots at different photon numbers share the call)
+            if devices is not None and len(devices) >= 1:
+                first = int(devices[0])
+                pmf_rows = lambda u, o, i: sampler_pmf(u, o, i, device=first)  # noqa: E731
+            else:
+                pmf_rows = sampler_pmf
         return _generate_samples_by_coroutines(input, shots, interferometer, seed_sequence,
                                                reject_condition, postselect_data,
-                                               uniform_particle_overlap,
-                                               pmf_rows or sampler_pmf)
+                                               uniform_particle_overlap, pmf_rows)
     input = np.asarray(input, dtype=int)
     U = np.ascontiguousarray(interferometer, dtype=np.complex128)
     d = len(input)
@@ -422,7 +440,8 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
         with ThreadPoolExecutor(max_workers=g) as pool:
             parts = list(pool.map(lambda job: run_batch(*job), jobs))
         return [smp for part in parts for smp in part]
-    device = int(devices[0]) if devices is not None and len(devices) == 1 else None
+    # fewer shots than devices, or a single device: everything on the first one
+    device = int(devices[0]) if devices is not None and len(devices) >= 1 else None
     # Shots are independent, so batches may also run concurrently on ONE device:
     # while one batch waits for the GPU inside the library call (GIL released,
     # device phases serialised by the library), another does its host bookkeeping
