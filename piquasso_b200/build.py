@@ -45,9 +45,12 @@ def _units():
         ("generic", "pqperm_kernels_generic.cu", []),
         # every FMA of the double-double arithmetic is explicit: no contraction
         ("arbiter", "pqperm_arbiter.cu", ["-fmad=false"]),
-        ("laplace_unit", "pqperm_kernels_laplace.cu", ["-DPQ_LAP_UNIT=1"]),
-        ("laplace_general", "pqperm_kernels_laplace.cu", ["-DPQ_LAP_UNIT=0"]),
     ]
+    # the batched Laplace walk: unit-column / general flavour x accumulation mode
+    for unit in (1, 0):
+        for mode in (0, 1, 2):
+            units.append(("laplace_u%d_m%d" % (unit, mode), "pqperm_kernels_laplace.cu",
+                          ["-DPQ_LAP_UNIT=%d" % unit, "-DPQ_LAP_MODE=%d" % mode]))
     for part, lo, hi in BINARY_PARTS:
         units.append((
             "binary%d" % part, "pqperm_kernels_binary.cu",

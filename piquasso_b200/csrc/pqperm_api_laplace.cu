@@ -186,6 +186,7 @@ struct Bucket {
     std::vector<LapWide> wide; // S = 32 only: column tables, aligned with probs
     std::vector<double> a2;   // packed mode
     int max_D = 0;
+    bool need_full = false;   // some problem has a zero-multiplicity column (it gets the full product)
 };
 
 // buckets[(S index) * 17 * 2 + NCL * 2 + unit]
@@ -208,6 +209,7 @@ struct Buckets {
             k.wide.clear();
             k.a2.clear();
             k.max_D = 0;
+            k.need_full = false;
         }
     }
 };
@@ -286,9 +288,18 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
     P.max_D = bk.max_D;
     const size_t smem = lap_smem_bytes(bk.max_D, bk.S, bk.NCL);
     PQ_CUDA(cudaEventRecord(c->lap_ev0, st));
-    cudaError_t e = launch_laplace(bk.S, bk.NCL, bk.unit, P, total_blocks, smem, st);
-    if (e != cudaSuccess)
-        return fail_cuda(e, "launch laplace_walk_kernel");
+    // accumulation mode of the walk: full product only (batched permanents), the
+    // leave-one-out sums, or both (a caller's zero-multiplicity column gets the full product)
+    const int mode = P.perm_only ? 2 : (bk.need_full ? 1 : 0);
+    cudaError_t e = launch_laplace(bk.S, bk.NCL, bk.unit, mode, P, total_blocks, smem, st);
+    if (e != cudaSuccess) {
+        const std::string what = "launch laplace_walk_kernel<NCL=" + std::to_string(bk.NCL) +
+                                 ", S=" + std::to_string(bk.S) + ", unit=" +
+                                 std::to_string((int)bk.unit) + ", mode=" + std::to_string(mode) +
+                                 "> grid=" + std::to_string(total_blocks) +
+                                 " smem=" + std::to_string(smem);
+        return fail_cuda(e, what.c_str());
+    }
     e = launch_laplace_reduce(P, ncp1, st);
     if (e != cudaSuccess)
         return fail_cuda(e, "launch laplace_reduce_kernel");
@@ -425,6 +436,8 @@ int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const
                 dst[((size_t)(d + 1) * NCP + j) * 2 + 1] = 2.0 * Ab[src + 1];
             }
         bk.max_D = std::max(bk.max_D, sh.D);
+        if (sh.NC < C[b])
+            bk.need_full = true;
         bk.probs.push_back(q);
         any = true;
     }

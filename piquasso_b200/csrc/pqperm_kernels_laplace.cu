@@ -1,15 +1,19 @@
 // pqperm_kernels_laplace.cu -- instantiations of the batched Laplace walk.
-// Compiled twice: -DPQ_LAP_UNIT=1 (all column multiplicities 1, what the
-// sampler issues for single-photon inputs) and -DPQ_LAP_UNIT=0 (general).
+// Compiled once per flavour: -DPQ_LAP_UNIT=1 (all column multiplicities 1, what the
+// sampler issues for single-photon inputs) or 0 (general), times -DPQ_LAP_MODE=0
+// (leave-one-out sums only), 1 (plus the full product) or 2 (full product only).
 #include <map>
 #include <mutex>
 
 #include "pqperm_launch.h"
 #include "pqperm_laplace.cuh"
 
-#ifndef PQ_LAP_UNIT
-#error "PQ_LAP_UNIT must be defined"
+#if !defined(PQ_LAP_UNIT) || !defined(PQ_LAP_MODE)
+#error "PQ_LAP_UNIT and PQ_LAP_MODE must be defined"
 #endif
+#define PQ_CONCAT3_(a, b, c, d) a##b##c##d
+#define PQ_CONCAT3(a, b, c, d) PQ_CONCAT3_(a, b, c, d)
+#define PQ_LAP_LAUNCHER PQ_CONCAT3(launch_laplace_u, PQ_LAP_UNIT, _m, PQ_LAP_MODE)
 
 namespace pqperm {
 
@@ -17,8 +21,9 @@ template <int NCL, int S>
 static cudaError_t launch_one(const LapParams &P, int total_blocks, size_t smem,
                               cudaStream_t stream)
 {
-    auto kernel = laplace_walk_kernel<NCL, S, PQ_LAP_UNIT != 0>;
-    if (smem > 48 * 1024) {
+    auto kernel = laplace_walk_kernel<NCL, S, PQ_LAP_UNIT != 0, PQ_LAP_MODE>;
+    // static (step tables, ~4.1 KB) + dynamic shared memory above 48 KB needs the opt-in
+    if (smem + 6 * 1024 > 48 * 1024) {
         static std::mutex mu;
         static std::map<int, size_t> raised; // device -> largest limit set
         int dev = 0;
@@ -36,11 +41,7 @@ static cudaError_t launch_one(const LapParams &P, int total_blocks, size_t smem,
     return cudaGetLastError();
 }
 
-#if PQ_LAP_UNIT
-cudaError_t launch_laplace_unit(
-#else
-cudaError_t launch_laplace_general(
-#endif
+cudaError_t PQ_LAP_LAUNCHER(
     int S, int NCL, const LapParams &P, int total_blocks, size_t smem, cudaStream_t stream)
 {
 #define PQ_CASE(SS, NN)                                                                 \
@@ -57,14 +58,21 @@ cudaError_t launch_laplace_general(
     return cudaErrorInvalidValue;
 }
 
-#if PQ_LAP_UNIT
-cudaError_t launch_laplace_general(int, int, const LapParams &, int, size_t, cudaStream_t);
+#if PQ_LAP_UNIT == 1 && PQ_LAP_MODE == 0
+#define PQ_DECL(u, m)                                                                   \
+    cudaError_t launch_laplace_u##u##_m##m(int, int, const LapParams &, int, size_t, cudaStream_t);
+PQ_DECL(0, 0) PQ_DECL(0, 1) PQ_DECL(0, 2) PQ_DECL(1, 1) PQ_DECL(1, 2)
+#undef PQ_DECL
 
-cudaError_t launch_laplace(int S, int NCL, bool unitcols, const LapParams &P,
+cudaError_t launch_laplace(int S, int NCL, bool unitcols, int mode, const LapParams &P,
                            int total_blocks, size_t smem, cudaStream_t stream)
 {
-    return unitcols ? launch_laplace_unit(S, NCL, P, total_blocks, smem, stream)
-                    : launch_laplace_general(S, NCL, P, total_blocks, smem, stream);
+#define PQ_GO(u, m)                                                                     \
+    if ((unitcols ? 1 : 0) == u && mode == m)                                           \
+        return launch_laplace_u##u##_m##m(S, NCL, P, total_blocks, smem, stream);
+    PQ_GO(0, 0) PQ_GO(0, 1) PQ_GO(0, 2) PQ_GO(1, 0) PQ_GO(1, 1) PQ_GO(1, 2)
+#undef PQ_GO
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_laplace_reduce(const LapParams &P, int ncp1, cudaStream_t stream)

@@ -186,7 +186,22 @@ __device__ __forceinline__ void dd_fold(double *tot, int slot, int nt, double v)
     *lo += e;
 }
 
-template <int NCL, int S, bool UNITCOLS>
+// MODE: what a term contributes to.  kLapLoo: the C leave-one-out sums only (the
+// sampler: every column of the compact problem has multiplicity >= 1);
+// kLapLooFull: also the full product, which the columns of the CALLER's matrix
+// with multiplicity 0 receive (reference quirk, src/permanent_laplace.cpp:180,210);
+// kLapPerm: the full product only (batched permanents).
+constexpr int kLapLoo = 0, kLapLooFull = 1, kLapPerm = 2;
+
+// One step of the low counter as the walk consumes it: byte offset of the row that
+// moves INTO local term m (relative to row 0 of the CTA's matrix) and the bit of
+// that digit in the threads' direction masks.
+struct LapStep {
+    unsigned rowoff;
+    unsigned bit;
+};
+
+template <int NCL, int S, bool UNITCOLS, int MODE>
 __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapParams P)
 {
     constexpr int NCP = NCL * S;
@@ -196,7 +211,7 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
     constexpr int CLEN = (NCL + CH - 1) / CH;              // longest chunk
     extern __shared__ double2 smA[];              // (D+1) x NCP, then the totals
     __shared__ double s_wtab[kLapMaxSegLen];
-    __shared__ uint8_t s_sched[kLapMaxSegLen];
+    __shared__ LapStep s_step[kLapMaxSegLen + 1];
     __shared__ int s_prob;
 
     // ---- which problem does this CTA belong to (binary search over first_block)
@@ -255,9 +270,14 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                 if (c != 0 && c != Q.mult[d])
                     w *= small_binom(Q.mult[d], c);
             }
-            s_sched[m] = (uint8_t)(p < 0 ? 0 : p);
+            // m = 0 has no move; entry W (the move out of the last term, applied to
+            // row sums nobody reads any more) is the pinned row with an empty bit
+            s_step[m] = LapStep{(unsigned)((p < 0 ? 0 : p + 1) * NCP * (int)sizeof(double2)),
+                                p < 0 ? 0u : 1u << p};
             s_wtab[m] = w;
         }
+        if (threadIdx.x == 0)
+            s_step[W] = LapStep{0u, 0u};
 #pragma unroll 4
         for (int k = 0; k < 4 * NCL + 4; k++)
             tot[k * NT] = 0.0;
@@ -267,13 +287,11 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
     const int h = threadIdx.x % S;                 // lane within the group
     const int groups_per_block = NT / S;
     const long long gstride = (long long)Q.nblocks * groups_per_block;
-    // sums of the current segment(s), plain FP64; folded into `tot` every segment
-    // (every kLapFoldTerms terms when the segments are shorter)
+    // sums of the current segment, plain FP64; folded into `tot` after every segment
     double accr[NCL], acci[NCL], fullr = 0.0, fulli = 0.0;
 #pragma unroll
     for (int j = 0; j < NCL; j++)
         accr[j] = acci[j] = 0.0;
-    int unfolded = 0;
 
     // All lanes of a warp run the same number of iterations (the group shuffles
     // below need the full warp); lanes past the last segment redo the last one
@@ -339,24 +357,23 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
             if (r & 1)
                 odd = 0;
         }
+        // weight of the segment's high digits; applied when the segment's sums are folded
         const double factor = valid ? (odd ? -bin : bin) : 0.0;
 
         // ---- walk
         // The move INTO term m+1 is applied column by column as soon as term m has
         // no further use for s_j: its 2*NCL independent FMAs and the row loads fill
         // latency gaps of the product chains instead of sitting in front of them.
-        int p_next = W > 1 ? s_sched[1] : 0;
+        // Per term the integer side is one table entry (row offset, digit bit), one
+        // bit test and one XOR: every instruction that is not FP64 still takes a
+        // dispatch slot from the FP64 pipe (ncu: 62 of them per term cost 12 % before).
+        const char *rows0 = reinterpret_cast<const char *>(smA + h);
         for (int m = 0; m < W; ++m) {
-            const double w = factor * s_wtab[m];
-            const bool more = m + 1 < W;
-            const int p = p_next;
-            const double sg = more ? (((dirmask >> p) & 1u) ? 1.0 : -1.0) : 0.0;
-            if (more)
-                dirmask ^= (1u << p) - 1u;
-            p_next = m + 2 < W ? s_sched[m + 2] : 0;
-            // row moved on the next step; after the last term the pinned row (always
-            // present, finite) times sg = 0 leaves s untouched
-            const double2 *row = smA + (more ? p + 1 : 0) * NCP + h;
+            const double w = s_wtab[m];
+            const LapStep st = s_step[m + 1];
+            const double sg = (dirmask & st.bit) ? 1.0 : -1.0;
+            dirmask ^= st.bit - 1u;
+            const double2 *row = reinterpret_cast<const double2 *>(rows0 + st.rowoff);
 
             if constexpr (UNITCOLS) {
                 // ---- product tree ---------------------------------------------------
@@ -367,7 +384,7 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                 double olr = 1.0, oli = 0.0; // other lanes (S > 1 only)
                 if (S > 1)
                     others_product<S>(lr, li, olr, oli);
-                if (P.perm_only) {
+                if constexpr (MODE == kLapPerm) {
                     // batched permanents: the product of ALL columns is the term
                     if (S > 1)
                         cmul(lr, li, olr, oli);
@@ -379,13 +396,12 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                         sr[j] = __fma_rn(sg, a.x, sr[j]);
                         si[j] = __fma_rn(sg, a.y, si[j]);
                     }
-                    continue;
-                }
-                if (S > 1) {
+                } else if (S > 1) {
                     // outside of the lane's root: w * other lanes; w * the product of
                     // ALL columns is what a c_l = 0 column gets
                     const double wor = w * olr, woi = w * oli;
-                    cfma(fullr, fulli, wor, woi, lr, li);
+                    if constexpr (MODE == kLapLooFull)
+                        cfma(fullr, fulli, wor, woi, lr, li);
                     if constexpr (NCL >= 2) {
                         tree_down<0, NCL, NCL, S, false>(sr, si, nr, ni, wor, woi, accr, acci,
                                                          row, sg);
@@ -394,15 +410,17 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                         acci[0] += woi;
                     }
                 } else {
-                    fullr = __fma_rn(w, lr, fullr);
-                    fulli = __fma_rn(w, li, fulli);
+                    if constexpr (MODE == kLapLooFull) {
+                        fullr = __fma_rn(w, lr, fullr);
+                        fulli = __fma_rn(w, li, fulli);
+                    }
                     if constexpr (NCL >= 2)
                         tree_down<0, NCL, NCL, S, true>(sr, si, nr, ni, w, 0.0, accr, acci, row,
                                                         sg);
                     else
                         accr[0] += w;
                 }
-                if constexpr (NCL == 1) {
+                if constexpr (NCL == 1 && MODE != kLapPerm) {
                     const double2 a = row[0];
                     sr[0] = __fma_rn(sg, a.x, sr[0]);
                     si[0] = __fma_rn(sg, a.y, si[0]);
@@ -452,7 +470,7 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
             double olr = 1.0, oli = 0.0; // other lanes (S > 1 only)
             if (S > 1)
                 others_product<S>(lr, li, olr, oli);
-            if (P.perm_only) {
+            if constexpr (MODE == kLapPerm) {
                 if (S > 1)
                     cmul(lr, li, olr, oli);
                 fullr = __fma_rn(w, lr, fullr);
@@ -463,8 +481,7 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                     sr[j] = __fma_rn(sg, a.x, sr[j]);
                     si[j] = __fma_rn(sg, a.y, si[j]);
                 }
-                continue;
-            }
+            } else {
             // start value of every chunk's prefix chain: w * other lanes * out_c.
             // Carrying w in the chain turns the accumulation into a complex FMA.
             double prer[CH], prei[CH];
@@ -477,15 +494,18 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                     if (CH > 1)
                         cmul(prer[c], prei[c], outr[c], outi[c]);
                 }
-                cfma(fullr, fulli, wor, woi, lr, li);
+                if constexpr (MODE == kLapLooFull)
+                    cfma(fullr, fulli, wor, woi, lr, li);
             } else {
 #pragma unroll
                 for (int c = 0; c < CH; c++) {
                     prer[c] = w * outr[c];
                     prei[c] = w * outi[c];
                 }
-                fullr = __fma_rn(w, lr, fullr);
-                fulli = __fma_rn(w, li, fulli);
+                if constexpr (MODE == kLapLooFull) {
+                    fullr = __fma_rn(w, lr, fullr);
+                    fulli = __fma_rn(w, li, fulli);
+                }
             }
             // prefix chains, interleaved over the chunks
 #pragma unroll
@@ -515,20 +535,27 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
                     }
                 }
             }
+            } // leave-one-out modes
             } // general flavour
         }
-        // ---- fold the segment sums into the double-double totals
-        unfolded += W;
-        if (unfolded >= kLapFoldTerms) {
-            unfolded = 0;
+        // ---- fold the segment's sums, times the weight of its high digits, into the
+        // double-double totals (the product acc * factor is split exactly)
+        auto fold = [&](int slot, double v) {
+            const double p = v * factor;
+            dd_fold(tot, slot, NT, p);
+            tot[(slot + 1) * NT] += __fma_rn(v, factor, -p);
+        };
+        if constexpr (MODE != kLapPerm) {
 #pragma unroll
             for (int j = 0; j < NCL; j++) {
-                dd_fold(tot, 4 * j, NT, accr[j]);
-                dd_fold(tot, 4 * j + 2, NT, acci[j]);
+                fold(4 * j, accr[j]);
+                fold(4 * j + 2, acci[j]);
                 accr[j] = acci[j] = 0.0;
             }
-            dd_fold(tot, 4 * NCL, NT, fullr);
-            dd_fold(tot, 4 * NCL + 2, NT, fulli);
+        }
+        if constexpr (MODE != kLapLoo) {
+            fold(4 * NCL, fullr);
+            fold(4 * NCL + 2, fulli);
             fullr = fulli = 0.0;
         }
     }

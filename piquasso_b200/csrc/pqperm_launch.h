@@ -39,7 +39,8 @@ cudaError_t launch_dfma_probe(int num_sms, int iters, double *sink, cudaStream_t
 
 namespace pqperm {
 
-cudaError_t launch_laplace(int S, int NCL, bool unitcols, const LapParams &P,
+// mode: 0 leave-one-out sums only, 1 plus the full product, 2 full product only
+cudaError_t launch_laplace(int S, int NCL, bool unitcols, int mode, const LapParams &P,
                            int total_blocks, size_t smem, cudaStream_t stream);
 cudaError_t launch_laplace_reduce(const LapParams &P, int ncp1, cudaStream_t stream);
 // pmf rows of the Clifford-Clifford sampler from the Laplace results of P (device)

@@ -45,7 +45,9 @@ inline cudaError_t resident_blocks(KernelT kernel, int NT, size_t smem, int *nb)
         *nb = it->second;
         return cudaSuccess;
     }
-    if (smem > 48 * 1024) {
+    // static (step tables of the n-ary walk, ~9.3 KB) + dynamic shared memory above
+    // 48 KB needs the opt-in
+    if (smem + 10 * 1024 > 48 * 1024) {
         size_t &limit = raised[std::make_pair((const void *)kernel, dev)];
         if (limit < smem) {
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

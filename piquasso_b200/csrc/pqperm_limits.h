@@ -27,7 +27,6 @@ constexpr int64_t kMaxSegLenNary = INT64_C(1) << 10;  // step tables live in sha
 
 constexpr int kLapMaxSegLen = 256;     // Laplace: terms per segment (tables in shared memory)
 constexpr int kLapThreads = 128;
-constexpr int kLapFoldTerms = 64;      // Laplace: plain-FP64 terms between double-double folds
 // Dynamic shared memory of one CTA of the Laplace walk: the (D+1) x NCP complex
 // matrix, then every thread's double-double totals (4 doubles per column of the
 // lane plus 4 for the full product).  Must fit beside ~2.3 KB of static tables.
