@@ -255,15 +255,23 @@ def main_arm(args):
                          "(use --impl reference for the host-core arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    nccl_log_dir = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL's own log is the evidence of the communicator (ranks, transport): keep
         # it visible.  Whatever the launcher set is left alone; otherwise the INIT
         # lines go to stderr, so that stdout stays the one JSON line.
         if "NCCL_DEBUG" not in os.environ:
+            import tempfile
             os.environ["NCCL_DEBUG"] = "INFO"
             os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+            if "NCCL_DEBUG_FILE" not in os.environ:
+                # one file per rank (NCCL re-opens whatever it is given, so it must not
+                # be /dev/stderr); rank 0 replays all of them at the end
+                nccl_log_dir = os.path.join(tempfile.gettempdir(),
+                                            "pq_nccl_%s" % os.environ.get("MASTER_PORT", "0"))
+                os.makedirs(nccl_log_dir, exist_ok=True)
+                os.environ["NCCL_DEBUG_FILE"] = os.path.join(nccl_log_dir, "rank%d.log" % rank)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -421,7 +429,19 @@ def main_arm(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        # printed last, after NCCL has said everything it had to say
+        if world > 1 and nccl_log_dir:
+            # NCCL's INIT log of every rank (communicator size, transports) on both
+            # streams, BEFORE the result: the JSON line stays the last line of stdout
+            time.sleep(0.5)
+            for r in range(world):
+                try:
+                    with open(os.path.join(nccl_log_dir, "rank%d.log" % r)) as fh:
+                        text = fh.read()
+                except OSError:
+                    continue
+                sys.stderr.write(text)
+                sys.stdout.write(text)
+            sys.stderr.flush()
         print(json.dumps(line), flush=True)
     return 0
 

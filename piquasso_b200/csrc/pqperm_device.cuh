@@ -141,6 +141,10 @@ template <int NT>
 __device__ __forceinline__ void finish_grid(const WalkParams &P, dd re, dd im)
 {
     __shared__ bool s_last;
+    if (gridDim.x == 1) { // nobody to wait for (the static path leaves the counters at zero)
+        block_reduce_store<NT>(re, im, P.out4);
+        return;
+    }
     block_reduce_store<NT>(re, im, P.partials + 4 * (size_t)blockIdx.x);
     if (threadIdx.x == 0) {
         __threadfence();

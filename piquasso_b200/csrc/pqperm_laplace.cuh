@@ -193,6 +193,12 @@ __device__ __forceinline__ void dd_fold(double *tot, int slot, int nt, double v)
 // kLapPerm: the full product only (batched permanents).
 constexpr int kLapLoo = 0, kLapLooFull = 1, kLapPerm = 2;
 
+// terms of the walk loop unrolled together (tuning knob; 1 = no unrolling)
+#ifndef PQ_LAP_UNROLL
+#define PQ_LAP_UNROLL 1
+#endif
+constexpr int kLapUnroll = PQ_LAP_UNROLL;
+
 // One step of the low counter as the walk consumes it: byte offset of the row that
 // moves INTO local term m (relative to row 0 of the CTA's matrix) and the bit of
 // that digit in the threads' direction masks.
@@ -368,6 +374,7 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
         // bit test and one XOR: every instruction that is not FP64 still takes a
         // dispatch slot from the FP64 pipe (ncu: 62 of them per term cost 12 % before).
         const char *rows0 = reinterpret_cast<const char *>(smA + h);
+#pragma unroll kLapUnroll
         for (int m = 0; m < W; ++m) {
             const double w = s_wtab[m];
             const LapStep st = s_step[m + 1];

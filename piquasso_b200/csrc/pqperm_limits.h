@@ -18,10 +18,11 @@ constexpr int kBinMaxBlockExp = 4;      // kernel 2: at most 2^4 terms per block
 // kernel 2: log2 of the terms per block for nc columns (register budget:
 // 4*nc for the row sums + 4 * 2^B for the running products)
 inline int binary_block_exponent(int /*nc*/) { return 3; }  // measured best for 20 <= nc <= 48
-// Below 2^kBinMinDigitsAuto terms the generic walk is used (measured on B200,
-// tools/r2_probe.py: n = 24 generic 127 us / binary 145 us, n = 26 generic 502 us /
-// binary 412 us).
-constexpr int kBinMinDigitsAuto = 25;
+// Below 2^kBinMinDigitsAuto terms the generic walk is used (B200 sweep over the
+// segment lengths, tools/r2_sweep.py, best kernel times generic / binary:
+// n = 20: 20.5 / 23.3 us, n = 22: 43.5 / 44.0, n = 24: 114.6 / 110.7, n = 25: 244 / 209,
+// n = 26: 450 / 364).
+constexpr int kBinMinDigitsAuto = 23;
 constexpr int64_t kMaxSegLenBinary = INT64_C(1) << 14;
 constexpr int64_t kMaxSegLenNary = INT64_C(1) << 10;  // step tables live in shared memory (9 KB)
 

@@ -174,7 +174,10 @@ int make_plan(const double *A, int R, int C, const int32_t *rows, const int32_t 
     const double ctas = std::max(1.0, std::min(32.0, std::floor(65536.0 / (nt * regs))));
     const double resident = std::min(2048.0, ctas * nt) * opt.num_sms;
     const double step = 2.0 * plan.NCP + 4.0 * plan.M + 2.0;
-    const double seed = 2.0 * plan.NCP * (plan.D + 1) + 40.0 * plan.D + 100.0;
+    // a seed is latency-bound (row after row through the constant bank / shared
+    // memory), not FMA-bound: weight from the B200 sweep tools/r2_sweep.py
+    const double seed = (plan.kernel == 2 ? 2.5 : 1.0) *
+                        (2.0 * plan.NCP * (plan.D + 1) + 40.0 * plan.D + 100.0);
     const int64_t wmax = (plan.binary && plan.unitcols) ? kMaxSegLenBinary : kMaxSegLenNary;
     const int qmin = plan.kernel == 2 ? plan.B : 0;
     int best_q = -1;

@@ -33,8 +33,19 @@ namespace pqperm {
 // the segment range is exhausted.  Returns this lane's segment, or -1 when the
 // range is exhausted (warp-uniform); the value may be >= P.seg_end in the last
 // batch.
-__device__ __forceinline__ long long next_batch(const WalkParams &P)
+//
+// A launch whose grid already holds one thread per segment (small problems: a
+// single partly filled wave) needs no dispenser at all: `round` 0 hands thread t of
+// the grid segment t, round 1 ends the loop -- two global atomic round trips less
+// on a path that is a few microseconds long.
+__device__ __forceinline__ long long next_batch(const WalkParams &P, int &round)
 {
+    const long long nseg = P.seg_end - P.seg_begin;
+    if ((long long)gridDim.x * blockDim.x >= nseg) {
+        if (round++ > 0)
+            return -1;
+        return P.seg_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    }
     unsigned long long base = 0;
     if ((threadIdx.x & 31) == 0)
         base = atomicAdd(P.counter, 32ull);
@@ -217,9 +228,10 @@ __global__ void __launch_bounds__(NT) perm_walk_generic(const __grid_constant__ 
     __syncthreads();
 
     dd totre{0.0, 0.0}, totim{0.0, 0.0};
+    int round = 0;
     for (;;) {
         // dynamic distribution: a warp takes the next 32 segments (see next_batch)
-        const long long seg = next_batch(P);
+        const long long seg = next_batch(P, round);
         if (seg < 0)
             break;
         if (seg >= P.seg_end)
@@ -326,8 +338,9 @@ __device__ __forceinline__ void binary_walk_body(const WalkParams &P, const doub
 
     dd totre{0.0, 0.0}, totim{0.0, 0.0};
     const int nblk = (int)(P.W >> B);
+    int round = 0;
     for (;;) {
-        const long long seg = next_batch(P);
+        const long long seg = next_batch(P, round);
         if (seg < 0)
             break;
         if (seg >= P.seg_end)

@@ -194,10 +194,22 @@ def generate_samples_sharded(input, shots, interferometer, seed_sequence,
             device_index = torch.cuda.current_device() if torch.cuda.is_available() else 0
         devices = [int(device_index)]
     mine = generate_samples(input, end - begin, interferometer, seed_sequence + begin,
-                            reject_condition=rejects, pmf_rows=pmf_rows, devices=devices)
-    if world == 1:
-        return mine
-    gathered = [None] * world
-    dist.all_gather_object(gathered, mine, group=group)
-    return [s for part in gathered for s in part]
-
+                            reject_condition=rejects, pmf_rows=pmf_rows, devices=devices,
+                            as_array=True)
+    if world > 1:
+        # one all-gather of the finished samples as an int32 array (rank shares padded
+        # to equal length) -- not pickled tuples
+        import torch
+        d = len(np.asarray(input))
+        per = -(-shots // world)
+        local = np.zeros((per, d), dtype=np.int32)
+        local[: end - begin] = mine
+        t = torch.from_numpy(local)
+        if dist.get_backend(group) == "nccl":
+            t = t.to("cuda:%d" % (devices[0] if devices else torch.cuda.current_device()))
+        gathered = torch.empty((world * per, d), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(gathered, t, group=group)
+        g = gathered.cpu().numpy().reshape(world, per, d)
+        mine = np.concatenate([g[r, : (shots * (r + 1)) // world - (shots * r) // world]
+                               for r in range(world)], axis=0)
+    return [tuple(row) for row in mine.tolist()]

@@ -310,7 +310,7 @@ def generate_lossy_samples(input, shots, interferometer, seed_sequence, postsele
 
 def generate_samples(input, shots, interferometer, seed_sequence, reject_condition=None,
                      batch_shots=None, postselect_data=None, uniform_particle_overlap=None,
-                     pmf_rows=None, overlap=1, devices=None):
+                     pmf_rows=None, overlap=1, devices=None, as_array=False):
     """Clifford & Clifford algorithm B, all shots in lock step.
 
     Restates ``_generate_samples`` / ``_generate_sample`` / ``_calculate_pmf``
@@ -350,7 +350,9 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
     last three photons, so it is off by default); ``batch_shots`` fixes the batch
     size instead.  ``devices`` (CUDA device indices) shards the shots over several
     GPUs inside this process, one host thread per device.  The result does not
-    depend on any of them.
+    depend on any of them.  ``as_array`` returns the samples as one (shots, d) int32
+    array instead of the reference's list of tuples (the sharded driver gathers
+    arrays, not pickled tuples).
     """
     import time
 
@@ -364,9 +366,10 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
                 pmf_rows = lambda u, o, i: sampler_pmf(u, o, i, device=first)  # noqa: E731
             else:
                 pmf_rows = sampler_pmf
-        return _generate_samples_by_coroutines(input, shots, interferometer, seed_sequence,
-                                               reject_condition, postselect_data,
-                                               uniform_particle_overlap, pmf_rows)
+        out = _generate_samples_by_coroutines(input, shots, interferometer, seed_sequence,
+                                              reject_condition, postselect_data,
+                                              uniform_particle_overlap, pmf_rows)
+        return np.array(out, dtype=np.int32).reshape(len(out), -1) if as_array else out
     input = np.asarray(input, dtype=int)
     U = np.ascontiguousarray(interferometer, dtype=np.complex128)
     d = len(input)
@@ -414,8 +417,11 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
             u = streams.random(live)
             _tick("host: rng.random", t0)
             t0 = time.perf_counter()
+            everyone = live.size == nb  # no rejected shot: hand the arrays over as they are
             if pmf_rows is None:
-                index = sampler_draw(U, sample[live], current_input[live], u, device=device)
+                index = sampler_draw(U, sample if everyone else sample[live],
+                                     current_input if everyone else current_input[live], u,
+                                     device=device)
                 _tick("pq_sampler_draw_c128 (filter + plan + GPU walk + pmf + draw)", t0)
             else:
                 pmf = pmf_rows(U, sample[live], current_input[live])
@@ -428,7 +434,11 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
                 index = (cdf <= u[:, None]).sum(axis=1)
                 _tick("host: normalise + search", t0)
             sample[live, index] += 1
-        return [tuple(row) for row in sample.tolist()]
+        return sample
+
+    def finish(parts):
+        arr = np.concatenate(parts, axis=0) if parts else np.zeros((0, d), dtype=np.int32)
+        return arr if as_array else [tuple(row) for row in arr.tolist()]
 
     if devices is not None and len(devices) > 1 and pmf_rows is None and shots >= len(devices):
         # one process, several GPUs: equal contiguous shot ranges, one host thread per
@@ -439,7 +449,7 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
                 for i, dev in enumerate(devices)]
         with ThreadPoolExecutor(max_workers=g) as pool:
             parts = list(pool.map(lambda job: run_batch(*job), jobs))
-        return [smp for part in parts for smp in part]
+        return finish(parts)
     # fewer shots than devices, or a single device: everything on the first one
     device = int(devices[0]) if devices is not None and len(devices) >= 1 else None
     # Shots are independent, so batches may also run concurrently on ONE device:
@@ -454,7 +464,7 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=overlap) as pool:
             parts = list(pool.map(lambda be: run_batch(be[0], be[1], device), bounds))
-    return [smp for part in parts for smp in part]
+    return finish(parts)
 
 
 # shots below which one batch is not worth splitting for host/GPU overlap

@@ -32,7 +32,7 @@ def test_plan_all_ones():
         assert p["flops_per_term"] == 8 * n + 2
         assert p["sum_rows"] == n and p["trivial"] == 0
     assert plan.plan(np.ones(40, int), np.ones(40, int))["kernel"] == 2
-    assert plan.plan(np.ones(26, int), np.ones(26, int))["kernel"] == 2
+    assert plan.plan(np.ones(24, int), np.ones(24, int))["kernel"] == 2
     assert plan.plan(np.ones(20, int), np.ones(20, int))["kernel"] == 1  # small: generic walk
     assert plan.plan([2, 1, 0, 3], [1, 1, 4, 0])["kernel"] == 1
 
