@@ -60,3 +60,26 @@ whole = permanent_laplace(a16, np.ones(15, int), np.ones(16, int))
 parts = sum(_laplace_device_partial(a16, np.ones(15, np.int32), np.ones(16, np.int32), g, 3) for g in range(3))
 assert np.allclose(parts, whole, rtol=1e-12)
 print("wide + laplace split ok")
+
+# round 2: the double-double arbiter, walks with more than one CTA (last-CTA reduction),
+# the Laplace accumulation modes (zero-multiplicity column -> full product; column
+# multiplicities -> chunked passes) and a sampler step
+from piquasso_b200 import arbiter
+for n in (10, 13):
+    U = unitary_group.rvs(n, random_state=n); ones = np.ones(n, np.int32)
+    hi, lo = arbiter.permanent_dd(U, ones, ones)
+    chk(hi, oracle.permanent(U, ones, ones, precision=1), ("arbiter", n))
+    chk(complex(permanent(U, ones, ones)), hi, ("walk after arbiter", n))
+hi, lo = arbiter.permanent_dd(unitary_group.rvs(6, random_state=6), rows, cols)
+chk(hi, oracle.permanent(unitary_group.rvs(6, random_state=6), rows, cols, precision=1), "arbiter n-ary")
+for n, choice in ((15, 1), (16, 32), (17, 22)):
+    U = unitary_group.rvs(n, random_state=n); ones = np.ones(n, np.int32)
+    lib.pq_set_kernel_choice(choice)
+    chk(complex(permanent(U, ones, ones)), oracle.permanent(U, ones, ones), ("multi-CTA", n, choice))
+lib.pq_set_kernel_choice(0)
+a5 = (rng.normal(size=(3, 6)) + 1j * rng.normal(size=(3, 6))) / 2
+for c5 in ([1, 0, 2, 1, 0, 1], [2, 2, 0, 0, 0, 1], [1, 1, 1, 1, 1, 0]):
+    r5 = rng.multinomial(sum(c5) - 1, np.ones(3) / 3)
+    got = permanent_laplace(a5, r5, c5); want = oracle.permanent_laplace(a5, r5, c5)
+    assert np.allclose(got, want, rtol=1e-8), ("laplace modes", c5)
+print("round-2 kernels ok, launches:", lib.pq_launch_count())
