@@ -130,10 +130,16 @@ def run(lib, peak_tflops, rank, world, local_rank, with_reference, sampler_shots
             ones = np.ones(n, dtype=np.int32)
             v, med, mn = _timed(lambda: entry(u, ones, ones), reps)
             kms = kernel_ms()
+            # the same call with the library's per-launch CUDA-event pair switched off
+            # (pq_set_timing(0): what a latency-sensitive caller would configure)
+            lib.pq_set_timing(0)
+            _, med_off, _ = _timed(lambda: entry(u, ones, ones), reps)
+            lib.pq_set_timing(1)
             terms = 2 ** (n - 1)
             flops = terms * (8 * n + 2)
             p = pqplan.plan(ones, ones)
             e = {"n": n, "terms": terms, "wall_ms": med * 1e3, "wall_ms_min": mn * 1e3,
+                 "wall_ms_timing_off": med_off * 1e3,
                  "kernel_ms": kms, "terms_per_s": terms / med, "binding": binding,
                  "plan": {"kernel": p["kernel"], "seg_len": p["seg_len"]},
                  "roofline": {"bound": "fp64", "achieved": flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
@@ -165,9 +171,13 @@ def run(lib, peak_tflops, rank, world, local_rank, with_reference, sampler_shots
             p = pqplan.plan(rows, cols)
             v, med, mn = _timed(lambda: entry(u60, rows, cols), 50)
             kms = kernel_ms()
+            lib.pq_set_timing(0)
+            _, med_off, _ = _timed(lambda: entry(u60, rows, cols), 50)
+            lib.pq_set_timing(1)
             flops = p["idx_max"] * p["flops_per_term"]
             e = {"idx_max": p["idx_max"], "flops_per_term": p["flops_per_term"],
-                 "wall_ms": med * 1e3, "wall_ms_min": mn * 1e3, "kernel_ms": kms,
+                 "wall_ms": med * 1e3, "wall_ms_min": mn * 1e3,
+                 "wall_ms_timing_off": med_off * 1e3, "kernel_ms": kms,
                  "plan": {"kernel": p["kernel"], "seg_len": p["seg_len"]},
                  "roofline": {"bound": "fp64", "achieved": flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
                               "peak": peak_tflops, "unit": "TFLOP/s", "frac": frac(flops, kms)}}

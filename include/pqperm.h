@@ -310,6 +310,11 @@ double pq_fp64_peak_tflops(int device, int iters);
  * 2 = force the binary constant-bank walk where applicable (tests / bench). */
 int pq_set_kernel_choice(int choice);
 
+/* Kernel timing of the permanent entries: on (default) every walk launch is
+ * bracketed by a CUDA event pair (pq_last_kernel_ms, pq_kernel_ms_history); off
+ * saves three driver calls (~4 us) per permanent and pq_last_kernel_ms reports -1. */
+int pq_set_timing(int on);
+
 /* Override the segment length exponent (0 = automatic): tests only. */
 int pq_set_seg_len_hint(int64_t seg_len);
 

@@ -108,6 +108,7 @@ SIGNATURES = [
     ("pq_sampler_work_reset", None, []),
     ("pq_fp64_peak_tflops", ctypes.c_double, [ctypes.c_int, ctypes.c_int]),
     ("pq_set_kernel_choice", ctypes.c_int, [ctypes.c_int]),
+    ("pq_set_timing", ctypes.c_int, [ctypes.c_int]),
     ("pq_set_seg_len_hint", ctypes.c_int, [ctypes.c_int64]),
 ]
 

@@ -6,8 +6,10 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -83,6 +85,7 @@ std::vector<std::unique_ptr<DeviceCtx>> g_ctx;
 std::vector<int> g_devices = {0};
 std::atomic<int64_t> g_launches{0};
 static int g_kernel_choice = 0;
+static bool g_timing = true; // CUDA-event pairs around the walk kernels (pq_set_timing)
 static int64_t g_seg_len_hint = 0;
 
 int ctx_get(int device, DeviceCtx **out)
@@ -281,7 +284,8 @@ static int launch_plan(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64_
     cudaError_t e;
     const bool fast = plan.binary && plan.unitcols;
     const int slot = (int)(c->ring_next % kTimingRing);
-    PQ_CUDA(cudaEventRecord(c->ring0[slot], stream));
+    if (g_timing)
+        PQ_CUDA(cudaEventRecord(c->ring0[slot], stream));
     if (plan.kernel == 2) {
         e = launch_binary(plan.NC, plan.B, P, rides_in_params(plan) ? plan.A2.data() : nullptr,
                           reinterpret_cast<const double2 *>(c->d_blob), c->num_sms, kMaxGrid,
@@ -291,8 +295,10 @@ static int launch_plan(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64_
     }
     if (e != cudaSuccess)
         return fail_cuda(e, plan.kernel == 2 ? "launch perm_walk_binary" : "launch perm_walk_generic");
-    PQ_CUDA(cudaEventRecord(c->ring1[slot], stream));
-    c->ring_next++;
+    if (g_timing) {
+        PQ_CUDA(cudaEventRecord(c->ring1[slot], stream));
+        c->ring_next++;
+    }
     g_launches += 1;
     return scratch_release(c, stream);
 }
@@ -309,6 +315,10 @@ static int enqueue_walk(const Plan &plan, DeviceCtx *c, int64_t seg_begin, int64
 // duration of the most recent launch_plan on c (its stream must be synchronised)
 static void note_last_kernel_ms(DeviceCtx *c)
 {
+    if (!g_timing) {
+        c->last_kernel_ms = -1.0;
+        return;
+    }
     if (c->ring_next == 0)
         return;
     const int slot = (int)((c->ring_next - 1) % kTimingRing);
@@ -367,6 +377,13 @@ extern "C" int pq_set_kernel_choice(int choice)
 {
     std::lock_guard<std::mutex> lock(g_mu);
     g_kernel_choice = choice;
+    return PQ_OK;
+}
+
+extern "C" int pq_set_timing(int on)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_timing = on != 0;
     return PQ_OK;
 }
 
@@ -489,12 +506,45 @@ extern "C" int pq_perm_gray_of_offset(int R, const int32_t *rows, int64_t offset
 }
 
 // Shared body of pq_perm_c128 / partial / segment sums.
+// PQ_HOST_PROFILE=1: where the host side of pq_perm_c128 spends its time (ns per
+// call, printed at exit): plan, context, enqueue (events + launch), wait, finish.
+namespace {
+struct HostProfile {
+    bool on = std::getenv("PQ_HOST_PROFILE") != nullptr;
+    double ns[5] = {0, 0, 0, 0, 0};
+    long calls = 0;
+    ~HostProfile()
+    {
+        if (on && calls)
+            std::fprintf(stderr,
+                         "pq host profile over %ld calls (us per call): plan %.2f, context %.2f, "
+                         "enqueue %.2f, wait %.2f, finish %.2f\n",
+                         calls, ns[0] / calls / 1e3, ns[1] / calls / 1e3, ns[2] / calls / 1e3,
+                         ns[3] / calls / 1e3, ns[4] / calls / 1e3);
+    }
+};
+HostProfile g_host_profile;
+struct HostLap {
+    std::chrono::steady_clock::time_point t;
+    HostLap() { if (g_host_profile.on) t = std::chrono::steady_clock::now(); }
+    void to(int slot)
+    {
+        if (!g_host_profile.on)
+            return;
+        const auto now = std::chrono::steady_clock::now();
+        g_host_profile.ns[slot] += std::chrono::duration<double, std::nano>(now - t).count();
+        t = now;
+    }
+};
+} // namespace
+
 static int perm_run(const double *A, int R, int C, const int32_t *rows, const int32_t *cols,
                     double out[2])
 {
     if (!out || (R > 0 && C > 0 && !A))
         return fail(PQ_ERR_BAD_ARG, "null pointer");
     std::lock_guard<std::mutex> lock(g_mu);
+    HostLap lap;
     {
         // more than PQ_MAX_COLS active columns (necessarily few rows): the
         // warp-per-segment batch walk, which holds up to 256 columns
@@ -518,6 +568,7 @@ static int perm_run(const double *A, int R, int C, const int32_t *rows, const in
             return PQ_OK;
         }
     }
+    lap.to(0);
     const std::vector<int> devices = g_devices;
     const int ndev = (int)devices.size();
     std::vector<DeviceCtx *> ctx(ndev, nullptr);
@@ -541,6 +592,7 @@ static int perm_run(const double *A, int R, int C, const int32_t *rows, const in
     dev_locks.reserve(used);
     for (int i = 0; i < used; i++)
         dev_locks.emplace_back(ctx[i]->mu);
+    lap.to(1);
     for (int i = 0; i < used; i++) {
         DeviceCtx *c = ctx[i];
         if (ndev > 1)
@@ -552,19 +604,24 @@ static int perm_run(const double *A, int R, int C, const int32_t *rows, const in
         if (rc)
             return rc;
     }
+    lap.to(2);
     double quads[4 * 64];
     for (int i = 0; i < used; i++) {
         DeviceCtx *c = ctx[i];
         if (ndev > 1)
             PQ_CUDA(cudaSetDevice(c->device));
         PQ_CUDA(cudaStreamSynchronize(c->stream));
+        lap.to(3);
         note_last_kernel_ms(c);
         for (int k = 0; k < 4; k++)
             quads[4 * i + k] = c->h_out[k];
     }
     double tot[4];
     pq_perm_combine(quads, used, tot); // fixed device order, error-free
-    return pq_perm_finish(tot, plan.sum_rows, out);
+    const int rc_fin = pq_perm_finish(tot, plan.sum_rows, out);
+    lap.to(4);
+    g_host_profile.calls++;
+    return rc_fin;
 }
 
 extern "C" int pq_perm_c128(const double *A, int R, int C, const int32_t *rows,

@@ -10,7 +10,8 @@ static cudaError_t launch_generic_nc(bool binary, bool unitcols, const WalkParam
                                      LaunchInfo *info)
 {
     constexpr int NT = NC <= 16 ? 128 : 64;
-    const size_t smem = (size_t)(P.D + 1) * NC * sizeof(double2);
+    // matrix, the two low-digit vectors, one common-seed buffer per warp
+    const size_t smem = (size_t)(P.D + 1 + 2 + NT / 32) * NC * sizeof(double2);
     if (binary && unitcols)
         return launch_walk(perm_walk_generic<NC, true, true, NT>, P, P, NT, smem, num_sms,
                            max_grid, stream, info);

@@ -57,38 +57,49 @@ __device__ __forceinline__ long long next_batch(const WalkParams &P, int &round)
 
 // ---- seeding: s_j, direction mask and weight of term(seg * W) ---------------
 // Restates the seed of src/permanent.cpp:174-202 for offset = seg * W.
+// ---- warp-cooperative seeding (generic walk) -----------------------------------
+// The 32 lanes of a warp hold 32 CONSECUTIVE segments: their Gray digits agree on
+// every high digit above the lowest few.  Instead of every lane summing all D rows
+// (D*NC loads and 2*D*NC FMAs per lane -- as much work as 8-16 terms, and what
+// small problems spend most of their time on), the warp evaluates the common
+// part once:
+//   * top-down over the high digits while all lanes carry the same weight: lane c
+//     accumulates column c (and c + 32) of  a_0 + sum_d w_d * row_d;
+//   * the remaining (varying) high digits are added per lane, row by row;
+//   * the common vector goes through a per-warp shared buffer to every lane;
+//   * the low digits (counter 0: g_d = 0 or r_d) contribute one of TWO vectors,
+//     selected by the lane's parity, tabulated once per CTA (`lowtab`).
+// Same terms, same partition; only the order of the additions inside a row sum
+// changes.  All 32 lanes must call it (votes, shuffles): lanes without a segment
+// pass a valid one and get their factor zeroed by the caller.
 template <int NC, bool BINARY>
-__device__ __forceinline__ void seed_segment(const WalkParams &P, const double2 *smA,
-                                             long long seg, double (&sr)[NC],
-                                             double (&si)[NC], unsigned &dirmask,
-                                             double &factor)
+__device__ __forceinline__ void seed_segment_coop(const WalkParams &P, const double2 *smA,
+                                                  const double2 *lowtab, double2 *cbuf,
+                                                  const double *binom, long long seg,
+                                                  double (&sr)[NC],
+                                                  double (&si)[NC], unsigned &dirmask,
+                                                  double &factor)
 {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NCW = (NC + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    double cx[NCW], cy[NCW];
 #pragma unroll
-    for (int j = 0; j < NC; j++) {
-        const double2 a = smA[j];
-        sr[j] = a.x;
-        si[j] = a.y;
+    for (int c = 0; c < NCW; c++) {
+        const int col = lane + 32 * c;
+        const double2 a = col < NC ? smA[col] : make_double2(0.0, 0.0);
+        cx[c] = a.x;
+        cy[c] = a.y;
     }
-    int odd = 0;
-    double bin = 1.0;
-    if (BINARY) {
-        // digits q..D-1 are the bits of seg; gray = seg ^ (seg >> 1)
-        const unsigned long long gh =
-            (unsigned long long)seg ^ ((unsigned long long)seg >> 1);
-        for (int d = P.D - 1; d >= P.q; --d) {
-            const int g = (int)((gh >> (d - P.q)) & 1ull);
-            const double w = g ? -0.5 : 0.5; // rows are stored doubled
-            const double2 *row = smA + (d + 1) * NC;
 #pragma unroll
-            for (int j = 0; j < NC; j++) {
-                const double2 a = row[j];
-                sr[j] = __fma_rn(w, a.x, sr[j]);
-                si[j] = __fma_rn(w, a.y, si[j]);
-            }
-        }
-        odd = __popcll(gh) & 1;
+    for (int j = 0; j < NC; j++)
+        sr[j] = si[j] = 0.0;
+
+    uint8_t chain[BINARY ? 1 : kMaxDigits];
+    unsigned long long gh = 0;
+    if (BINARY) {
+        gh = (unsigned long long)seg ^ ((unsigned long long)seg >> 1);
     } else {
-        uint8_t chain[kMaxDigits];
         unsigned long long rest = (unsigned long long)seg;
         for (int d = P.q; d < P.D; ++d) {
             const unsigned L = P.radix[d];
@@ -101,13 +112,37 @@ __device__ __forceinline__ void seed_segment(const WalkParams &P, const double2 
                 rest = r32 / L;
             }
         }
-        for (int d = P.D - 1; d >= P.q; --d) {
+    }
+    int odd = 0;
+    double bin = 1.0;
+    bool common = true; // warp-uniform: still inside the prefix of digits all lanes share
+    for (int d = P.D - 1; d >= P.q; --d) {
+        double w;
+        if (BINARY) {
+            const int g = (int)((gh >> (d - P.q)) & 1ull);
+            odd ^= g;
+            w = g ? -0.5 : 0.5; // rows are stored doubled
+        } else {
             const int r = P.mult[d];
             const int g = odd ? r - chain[d] : chain[d];
             odd ^= (g & 1);
-            bin *= P.binom[P.binom_off[d] + g];
-            const double w = 0.5 * (double)(r - 2 * g);
-            const double2 *row = smA + (d + 1) * NC;
+            bin *= binom[P.binom_off[d] + g];
+            w = 0.5 * (double)(r - 2 * g);
+        }
+        if (common)
+            common = __all_sync(FULL, w == __shfl_sync(FULL, w, 0));
+        const double2 *row = smA + (d + 1) * NC;
+        if (common) {
+#pragma unroll
+            for (int c = 0; c < NCW; c++) {
+                const int col = lane + 32 * c;
+                if (col < NC) {
+                    const double2 a = row[col];
+                    cx[c] = __fma_rn(w, a.x, cx[c]);
+                    cy[c] = __fma_rn(w, a.y, cy[c]);
+                }
+            }
+        } else {
 #pragma unroll
             for (int j = 0; j < NC; j++) {
                 const double2 a = row[j];
@@ -116,23 +151,54 @@ __device__ __forceinline__ void seed_segment(const WalkParams &P, const double2 
             }
         }
     }
+    // the common vector: through this warp's buffer to every lane
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < NCW; c++) {
+        const int col = lane + 32 * c;
+        if (col < NC)
+            cbuf[col] = make_double2(cx[c], cy[c]);
+    }
+    __syncwarp();
+    const double2 *low = lowtab + (odd ? NC : 0);
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+        const double2 a = cbuf[j], l = low[j];
+        sr[j] += a.x + l.x;
+        si[j] += a.y + l.y;
+    }
     // low digits: counter digits are 0, so g_d = 0 (even prefix) or r_d (odd)
     dirmask = 0;
     for (int d = P.q - 1; d >= 0; --d) {
         const int r = BINARY ? 1 : P.mult[d];
         dirmask |= (unsigned)odd << d;
-        const double w = odd ? -0.5 * (double)r : 0.5 * (double)r;
-        const double2 *row = smA + (d + 1) * NC;
-#pragma unroll
-        for (int j = 0; j < NC; j++) {
-            const double2 a = row[j];
-            sr[j] = __fma_rn(w, a.x, sr[j]);
-            si[j] = __fma_rn(w, a.y, si[j]);
-        }
         if (r & 1)
             odd = 0; // g_d = r_d odd flips the parity seen by the digits below
     }
     factor = odd ? -bin : bin;
+}
+
+// The two low-digit vectors of seed_segment_coop: lowtab[o * NC + j] =
+// sum_{d < q} w_d(o) * row_d[j] for a segment entered with parity o.
+template <int NC, bool BINARY, int NT>
+__device__ __forceinline__ void build_lowtab(const WalkParams &P, const double2 *smA,
+                                             double2 *lowtab)
+{
+    for (int t = threadIdx.x; t < 2 * NC; t += NT) {
+        int odd = t / NC;
+        const int j = t - odd * NC;
+        double x = 0.0, y = 0.0;
+        for (int d = P.q - 1; d >= 0; --d) {
+            const int r = BINARY ? 1 : P.mult[d];
+            const double w = odd ? -0.5 * (double)r : 0.5 * (double)r;
+            const double2 a = smA[(d + 1) * NC + j];
+            x = __fma_rn(w, a.x, x);
+            y = __fma_rn(w, a.y, y);
+            if (r & 1)
+                odd = 0;
+        }
+        lowtab[t] = make_double2(x, y);
+    }
 }
 
 // ---- prod_j s_j^{c_j} ------------------------------------------------------
@@ -194,10 +260,19 @@ __device__ __forceinline__ dd dd_scale(const dd &a, double f)
 // mask update.  The binomial weight of the low digits is the same for every
 // thread (C(r,g) = C(r,r-g)), so it comes from the host-built wtab[m]; the
 // thread's own high-digit weight is applied once per segment.
+//
+// The matrix is staged in shared memory from the uploaded blob.  (Measured on B200
+// and rejected: the matrix in the kernel's parameter block.  Walking it there costs
+// register-indexed LDC.64 loads, twice as slow as uniform LDS.128 -- n = 24: 127 ->
+// 213 us; staging it from there costs divergent constant loads -- config 3: 86 ->
+// 108 us.  One 6 KB H2D copy is cheaper than either.)
 template <int NC, bool BINARY, bool UNITCOLS, int NT>
-__global__ void __launch_bounds__(NT) perm_walk_generic(const __grid_constant__ WalkParams P)
+__device__ __forceinline__ void generic_walk_body(const WalkParams &P, const double2 *src,
+                                                  const double *binom)
 {
-    extern __shared__ double2 smA[];
+    extern __shared__ double2 smA[]; // (D+1) x NC matrix, 2 x NC low vectors, NC per warp
+    double2 *lowtab = smA + (P.D + 1) * NC;
+    double2 *cbuf = lowtab + 2 * NC + (threadIdx.x >> 5) * NC;
     // step tables of the low counter (n-ary only), built by the CTA itself: the
     // digit moved on the step into m and (-1)^m prod_{d<q} C(r_d, c_d(m)).  In
     // shared memory they cost one LDS per step; nothing is uploaded for them.
@@ -207,7 +282,9 @@ __global__ void __launch_bounds__(NT) perm_walk_generic(const __grid_constant__ 
     {
         const int nelem = (P.D + 1) * NC;
         for (int i = threadIdx.x; i < nelem; i += NT)
-            smA[i] = P.A2[i];
+            smA[i] = src[i];
+        __syncthreads();
+        build_lowtab<NC, BINARY, NT>(P, smA, smA + (P.D + 1) * NC);
         if (!BINARY) {
             for (int m = threadIdx.x; m < W; m += NT) {
                 int rest = m, p = -1;
@@ -218,7 +295,7 @@ __global__ void __launch_bounds__(NT) perm_walk_generic(const __grid_constant__ 
                     rest /= L;
                     if (p < 0 && c != 0)
                         p = d;
-                    w *= P.binom[P.binom_off[d] + c];
+                    w *= binom[P.binom_off[d] + c];
                 }
                 s_sched[m] = (uint8_t)(p < 0 ? 0 : p);
                 s_wtab[m] = w;
@@ -231,15 +308,22 @@ __global__ void __launch_bounds__(NT) perm_walk_generic(const __grid_constant__ 
     int round = 0;
     for (;;) {
         // dynamic distribution: a warp takes the next 32 segments (see next_batch)
-        const long long seg = next_batch(P, round);
-        if (seg < 0)
+        const long long seg_drawn = next_batch(P, round);
+        if (seg_drawn < 0)
             break;
-        if (seg >= P.seg_end)
+        // the whole warp seeds together: lanes past the range redo the last segment
+        // with weight 0
+        const bool valid = seg_drawn < P.seg_end;
+        if (__all_sync(0xffffffffu, !valid))
             continue;
+        const long long seg = valid ? seg_drawn : P.seg_end - 1;
         double sr[NC], si[NC];
         unsigned dirmask;
         double factor;
-        seed_segment<NC, BINARY>(P, smA, seg, sr, si, dirmask, factor);
+        seed_segment_coop<NC, BINARY>(P, smA, lowtab, cbuf, binom, seg, sr, si, dirmask,
+                                      factor);
+        if (!valid)
+            factor = 0.0;
 
         dd segre{0.0, 0.0}, segim{0.0, 0.0};
         constexpr int CHUNK = 64;
@@ -279,7 +363,7 @@ __global__ void __launch_bounds__(NT) perm_walk_generic(const __grid_constant__ 
         }
         segre = dd_scale(segre, factor);
         segim = dd_scale(segim, factor);
-        if (P.segsums) {
+        if (P.segsums && valid) {
             P.segsums[2 * (seg - P.seg_begin)] = segre.hi + segre.lo;
             P.segsums[2 * (seg - P.seg_begin) + 1] = segim.hi + segim.lo;
         }
@@ -287,6 +371,12 @@ __global__ void __launch_bounds__(NT) perm_walk_generic(const __grid_constant__ 
         dd_add(totim, segim);
     }
     finish_grid<NT>(P, totre, totim);
+}
+
+template <int NC, bool BINARY, bool UNITCOLS, int NT>
+__global__ void __launch_bounds__(NT) perm_walk_generic(const __grid_constant__ WalkParams P)
+{
+    generic_walk_body<NC, BINARY, UNITCOLS, NT>(P, P.A2, P.binom);
 }
 
 #ifndef PQ_COL_CHUNK
