@@ -167,6 +167,13 @@ int pq_sampler_draw_dev_c128(int device, const double *U, int d, int nshots,
 int pq_sampler_pmf_dev_c128(int device, const double *U, int d, int nshots,
                             const int32_t *out_occ, const int32_t *in_occ, double *pmf);
 
+/* Host helper of the sampler (no GPU involved): the raw 64-bit streams of the numpy
+ * generators the reference gives its shots, np.random.default_rng(seed0 + i) for
+ * i in [0, n) (piquasso/_simulators/passive/sampling.py:149-194), `draws` outputs
+ * each: out[i * draws + k] == np.random.PCG64(seed0 + i).random_raw(draws)[k].
+ * Restates numpy's SeedSequence + PCG64 seeding for integer seeds below 2^64. */
+int pq_pcg64_streams(uint64_t seed0, int64_t n, int draws, uint64_t *out);
+
 /* Where the calling thread's last pq_sampler_* call spent its wall time, in
  * milliseconds: out_ms[0] planning on the host (zero filtering, problem
  * descriptors), [1] waiting for the device's lock, [2] the device phase (uploads,

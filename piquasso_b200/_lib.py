@@ -71,6 +71,8 @@ SIGNATURES = [
      [c_double_p, ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, c_double_p]),
     ("pq_sampler_draw_c128", ctypes.c_int,
      [c_double_p, ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, c_double_p, c_int32_p]),
+    ("pq_pcg64_streams", ctypes.c_int,
+     [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_uint64)]),
     ("pq_last_sampler_profile", None, [c_double_p]),
     ("pq_sampler_draw_dev_c128", ctypes.c_int,
      [ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, c_double_p,

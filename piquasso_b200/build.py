@@ -42,6 +42,7 @@ def _units():
         ("api", "pqperm_api.cu", []),
         ("api_laplace", "pqperm_api_laplace.cu", []),
         ("plan", "pqperm_plan.cpp", []),
+        ("rng", "pqperm_rng.cpp", []),
         ("generic", "pqperm_kernels_generic.cu", []),
         # every FMA of the double-double arithmetic is explicit: no contraction
         ("arbiter", "pqperm_arbiter.cu", ["-fmad=false"]),

@@ -5,6 +5,7 @@
 // no CUDA device is usable every compute entry returns PQ_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -140,6 +141,16 @@ int ctx_get(int device, DeviceCtx **out)
     return PQ_OK;
 }
 
+// Grow-only scratch of the batched Laplace / sampler path.  The FIRST allocation of a
+// slot is at least its floor, sized for a 10^4-shot, 100-mode sampler run: regrowing
+// (free + allocate; pinning megabytes of host memory) was measured to take up to
+// 0.47 s now and then on the GPU box (tools/diag_sampler2.py: 2 of 8 fresh processes),
+// which a run pays once, at its first small call, instead of in the middle of its first
+// large one.
+static const size_t kDevFloor[9] = {8u << 20, 1u << 20, 32u << 20, 16u << 20, 1u << 20,
+                                    16u << 20, 1u << 20, 1u << 20, 1u << 20};
+static const size_t kHostFloor[5] = {1u << 20, 1u << 20, 16u << 20, 16u << 20, 8u << 20};
+
 int grow_dev(DeviceCtx *c, int slot, size_t bytes)
 {
     if (c->d_lap_cap[slot] >= bytes)
@@ -150,7 +161,7 @@ int grow_dev(DeviceCtx *c, int slot, size_t bytes)
         c->u_host.clear(); // the resident interferometer goes with its buffer
     c->d_lap[slot] = nullptr;
     c->d_lap_cap[slot] = 0;
-    const size_t cap = bytes + bytes / 2 + 4096;
+    const size_t cap = std::max(bytes + bytes / 2 + 4096, kDevFloor[slot]);
     PQ_CUDA(cudaMalloc(&c->d_lap[slot], cap));
     c->d_lap_cap[slot] = cap;
     return PQ_OK;
@@ -164,7 +175,7 @@ int grow_host(DeviceCtx *c, int slot, size_t bytes)
         cudaFreeHost(c->h_lap[slot]);
     c->h_lap[slot] = nullptr;
     c->h_lap_cap[slot] = 0;
-    const size_t cap = bytes + bytes / 2 + 4096;
+    const size_t cap = std::max(bytes + bytes / 2 + 4096, kHostFloor[slot]);
     PQ_CUDA(cudaMallocHost(&c->h_lap[slot], cap));
     c->h_lap_cap[slot] = cap;
     return PQ_OK;

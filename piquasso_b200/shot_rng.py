@@ -34,20 +34,47 @@ class ShotStreams:
     ``[begin, end)``, addressed by shot number ``0 .. end-begin-1``."""
 
     def __init__(self, seed_sequence, begin, end, draws_per_shot):
-        self._bitgens = [np.random.PCG64(seed_sequence + idx) for idx in range(begin, end)]
-        n = len(self._bitgens)
+        n = max(0, end - begin)
         self._chunk = max(4, int(draws_per_shot))
-        self._raw = np.empty((n, self._chunk), dtype=np.uint64)
-        for i, bg in enumerate(self._bitgens):
-            self._raw[i] = bg.random_raw(self._chunk)
+        self._seed0 = seed_sequence + begin
+        self._bitgens = None
+        self._raw = self._bulk(n, self._chunk)
+        if self._raw is None:
+            # seeds the library does not restate (negative, >= 2**64, not an int): real
+            # numpy bit generators, one per shot
+            self._bitgens = [np.random.PCG64(seed_sequence + idx) for idx in range(begin, end)]
+            self._raw = np.empty((n, self._chunk), dtype=np.uint64)
+            for i, bg in enumerate(self._bitgens):
+                self._raw[i] = bg.random_raw(self._chunk)
         self._pos = np.zeros(n, dtype=np.int64)       # next unread raw output
         self._has32 = np.zeros(n, dtype=bool)         # PCG64's pending high half
         self._buf32 = np.zeros(n, dtype=np.uint64)
+
+    def _bulk(self, n, draws):
+        """All shots' first `draws` raw outputs from ONE library call
+        (``pq_pcg64_streams``: numpy's SeedSequence + PCG64 restated on the host,
+        threaded), or None when the seeds are outside what it restates."""
+        import ctypes
+
+        from . import _lib
+        seed0 = self._seed0
+        if not isinstance(seed0, (int, np.integer)) or seed0 < 0 or seed0 + n >= (1 << 64):
+            return None
+        out = np.empty((n, draws), dtype=np.uint64)
+        rc = _lib.load().pq_pcg64_streams(
+            ctypes.c_uint64(int(seed0)), n, draws,
+            out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
+        return out if rc == 0 else None
 
     # -- raw outputs ---------------------------------------------------------
     def _ensure(self, shots, count=1):
         """Make sure `count` more raw outputs exist for the given shots."""
         while (self._pos[shots] + count > self._raw.shape[1]).any():
+            have = self._raw.shape[1]
+            if self._bitgens is None:
+                # the streams are pure functions of the seeds: regenerate, longer
+                self._raw = self._bulk(self._raw.shape[0], have + self._chunk)
+                continue
             more = np.empty((self._raw.shape[0], self._chunk), dtype=np.uint64)
             for i, bg in enumerate(self._bitgens):
                 more[i] = bg.random_raw(self._chunk)

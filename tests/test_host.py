@@ -396,3 +396,29 @@ def test_sampler_edge_cases_on_the_host():
     for smp in generate_lossy_samples([1, 0, 1, 0], 5, 0.7 * u, 1, **kw):
         assert len(smp) == 4 and sum(smp) <= 2
     assert len(generate_samples([3, 0, 0, 0], 2, u, 1, devices=[0], **kw)) == 2
+
+
+def test_bulk_pcg64_streams_equal_numpy_bit_generators(lib):
+    """pq_pcg64_streams restates numpy's SeedSequence + PCG64 seeding on the host: raw
+    outputs identical to np.random.PCG64(seed).random_raw for seeds on both sides of
+    the 32-bit word boundary and up to 2^64 (the per-shot generators of the reference's
+    sampler, piquasso/_simulators/passive/sampling.py:149-194)."""
+    import ctypes
+    for seed0, n, draws in ((0, 5, 3), (123, 64, 17), (2 ** 32 - 40, 80, 5), (2 ** 47 + 1, 9, 60),
+                            (2 ** 64 - 12, 11, 4)):
+        out = np.empty((n, draws), dtype=np.uint64)
+        rc = lib.pq_pcg64_streams(ctypes.c_uint64(seed0), n, draws,
+                                  out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
+        assert rc == 0
+        want = np.array([np.random.PCG64(seed0 + i).random_raw(draws) for i in range(n)])
+        assert np.array_equal(out, want), seed0
+    # seeds the library does not restate fall back to real numpy generators
+    from piquasso_b200.shot_rng import ShotStreams
+    big = ShotStreams(2 ** 70, 0, 3, 4)
+    want = np.random.default_rng(2 ** 70 + 1).random()
+    assert big.random(np.array([1]))[0] == want
+    # a stream that runs out of its first chunk is regenerated, longer, identically
+    s = ShotStreams(7, 0, 4, 4)
+    rng = np.random.default_rng(7 + 2)
+    for _ in range(20):
+        assert s.random(np.array([2]))[0] == rng.random()
