@@ -371,7 +371,8 @@ def test_sampler_batch_bounds():
     assert _batch_bounds(0, None, 1) == []
     assert _batch_bounds(10, 4, 1) == [(0, 4), (4, 8), (8, 10)]
     assert _batch_bounds(500, None, 2) == [(0, 500)]  # too few shots to split
-    bounds = _batch_bounds(10000, None, 2)
+    assert _batch_bounds(10001, None, 2) == [(0, 5000), (5000, 10001)]  # two halves
+    bounds = _batch_bounds(10000, None, 3)
     assert bounds[0][0] == 0 and bounds[-1][1] == 10000 and len(bounds) == 4
     assert all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
 
