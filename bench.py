@@ -261,7 +261,9 @@ def main_arm(args):
         # NCCL's own log is the evidence of the communicator (ranks, transport): keep
         # it visible.  Whatever the launcher set is left alone; otherwise the INIT
         # lines go to stderr, so that stdout stays the one JSON line.
-        if "NCCL_DEBUG" not in os.environ:
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            # unset, or a level that says nothing about the communicator (the image
+            # presets VERSION): raise it to INFO for the INIT subsystem only
             import tempfile
             os.environ["NCCL_DEBUG"] = "INFO"
             os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")

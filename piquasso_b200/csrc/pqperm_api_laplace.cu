@@ -35,7 +35,7 @@ constexpr long long kLapBigProblem = 1LL << 18;       // terms
 // the sampler step plans its shots on up to this many host threads ...
 constexpr int kPlanThreadsMax = 8;
 // ... as long as every thread gets at least this many shots
-constexpr int kPlanShotsPerThread = 1024;
+constexpr int kPlanShotsPerThread = 256;
 
 // Finer split of the device phase of the calling thread's last sampler step (ms):
 // [0] scratch growth, [1] staging into pinned memory, [2] enqueueing (copies,
