@@ -100,6 +100,17 @@ int pq_perm_laplace_partial_c128(const double *A, int R, int C, const int32_t *r
                                  const int32_t *cols, int part, int nparts, double *out,
                                  int *out_len);
 
+/* The same with the rank's partial sums LEFT ON THE DEVICE: d_out (memory of
+ * `device`, 2*C doubles, layout of pq_perm_laplace_c128) is written by the library's
+ * stream and the call returns after that stream has been synchronised, so the
+ * caller can hand d_out straight to the collective (ncclAllGather / all-reduce)
+ * without a trip through the host.  *out_len = C, or 1 on the reference's early-out;
+ * trivial[2] is NaN unless the problem was that early-out, in which case it holds the
+ * value (part 0: 1, others: 0) and d_out is untouched. */
+int pq_perm_laplace_partial_dev_c128(const double *A, int R, int C, const int32_t *rows,
+                                     const int32_t *cols, int part, int nparts, int device,
+                                     double *d_out, double *trivial, int *out_len);
+
 /* ---------------------------------------------------------------------
  * Batch of independent permanent_laplace problems in one call (what the
  * Clifford-Clifford sampler issues once per photon per shot,

@@ -59,6 +59,9 @@ SIGNATURES = [
     ("pq_perm_laplace_partial_c128", ctypes.c_int,
      [c_double_p, ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, ctypes.c_int, ctypes.c_int,
       c_double_p, ctypes.POINTER(ctypes.c_int)]),
+    ("pq_perm_laplace_partial_dev_c128", ctypes.c_int,
+     [c_double_p, ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, ctypes.c_int, ctypes.c_int,
+      ctypes.c_int, ctypes.c_void_p, c_double_p, ctypes.POINTER(ctypes.c_int)]),
     ("pq_perm_laplace_c64", ctypes.c_int,
      [c_float_p, ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, c_float_p,
       ctypes.POINTER(ctypes.c_int)]),

@@ -224,6 +224,11 @@ struct Epilogue {
     const double *u = nullptr;    // sampler draw: host [nshots] uniform variates ...
     int32_t *index = nullptr;     // ... and the drawn output modes (the pmf stays on the device)
     bool perm_only = false;       // batched permanents: only the full product
+    // single problem whose results stay on the device: d_dst[j] = result of compact
+    // column map[j] (ncols entries, map on the host), nothing is downloaded
+    double *d_dst = nullptr;
+    const int32_t *map = nullptr;
+    int ncols = 0;
 };
 
 // One bucket = one walk launch + one reduce launch (+ pmf epilogue).  Without
@@ -341,6 +346,19 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
         g_launches += 1;
         h_dst = c->h_lap[3];
         d_src = c->d_lap[5];
+    } else if (epi && epi->d_dst) {
+        // results stay on the device: scatter compact -> caller's columns there
+        const size_t mbytes = (size_t)epi->ncols * sizeof(int32_t);
+        if ((rc = grow_dev(c, 7, mbytes)) || (rc = grow_host(c, 1, mbytes)))
+            return rc;
+        std::memcpy(c->h_lap[1], epi->map, mbytes);
+        PQ_CUDA(cudaMemcpyAsync(c->d_lap[7], c->h_lap[1], mbytes, cudaMemcpyHostToDevice, st));
+        e = launch_laplace_scatter(reinterpret_cast<const double2 *>(c->d_lap[3]),
+                                   reinterpret_cast<const int *>(c->d_lap[7]), epi->ncols,
+                                   reinterpret_cast<double2 *>(epi->d_dst), st);
+        if (e != cudaSuccess)
+            return fail_cuda(e, "launch laplace_scatter_kernel");
+        g_launches += 1;
     } else {
         bytes = out_bytes;
         if ((rc = grow_host(c, 2, bytes)))
@@ -349,7 +367,8 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
         d_src = c->d_lap[3];
     }
     PQ_CUDA(cudaEventRecord(c->lap_ev1, st));
-    PQ_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    if (bytes)
+        PQ_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
     lap.to(g_sampler_detail[2]);
     PQ_CUDA(cudaStreamSynchronize(st));
     lap.to(g_sampler_detail[3]);
@@ -375,8 +394,11 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
 int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const int32_t *R,
                          const int32_t *C, const int32_t *rows, const int64_t *r_off,
                          const int32_t *cols, const int64_t *c_off, double *out,
-                         const int64_t *o_off, int32_t *out_len, int part = 0, int nparts = 1)
+                         const int64_t *o_off, int32_t *out_len, int part = 0, int nparts = 1,
+                         int device = -1, double *d_out = nullptr)
 {
+    // d_out (device, 2 * C[0] doubles; nprob must be 1): leave the results there instead
+    // of `out`; trivial problems are still answered on the host (out_len = 1)
     std::string err;
     LapShape sh;
     g_buckets.reset();
@@ -444,7 +466,7 @@ int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const
     if (!any)
         return PQ_OK;
     DeviceCtx *c = nullptr;
-    int rc = ctx_get(g_devices[0], &c);
+    int rc = ctx_get(device >= 0 ? device : g_devices[0], &c);
     if (rc)
         return rc;
     std::lock_guard<std::mutex> dev_lock(c->mu);
@@ -452,6 +474,23 @@ int laplace_batch_locked(int nprob, const double *A, const int64_t *a_off, const
     for (Bucket &bk : g_buckets.b) {
         if (bk.probs.empty())
             continue;
+        if (d_out) {
+            // one problem, results scattered on the device
+            const int NCPd = bk.S * bk.NCL;
+            std::vector<int32_t> map((size_t)C[0]);
+            const int32_t *cm = cols + c_off[0];
+            int k = 0;
+            for (int j = 0; j < C[0]; j++)
+                map[j] = cm[j] > 0 ? k++ : NCPd;
+            Epilogue epi;
+            epi.d_dst = d_out;
+            epi.map = map.data();
+            epi.ncols = C[0];
+            rc = run_bucket(c, bk, &epi);
+            if (rc)
+                return rc;
+            continue;
+        }
         rc = run_bucket(c, bk, nullptr);
         if (rc)
             return rc;
@@ -972,6 +1011,31 @@ extern "C" int pq_perm_laplace_partial_c128(const double *A, int R, int C, const
     if (rc)
         return rc;
     *out_len = len;
+    return PQ_OK;
+}
+
+extern "C" int pq_perm_laplace_partial_dev_c128(const double *A, int R, int C,
+                                                const int32_t *rows, const int32_t *cols,
+                                                int part, int nparts, int device,
+                                                double *d_out, double *trivial, int *out_len)
+{
+    if (!d_out || !out_len || !trivial || (R > 0 && C > 0 && !A))
+        return fail(PQ_ERR_BAD_ARG, "null pointer");
+    if (R < 0 || C < 0 || nparts < 1 || part < 0 || part >= nparts || device < 0)
+        return fail(PQ_ERR_BAD_ARG, "bad shape, part index or device");
+    const int64_t zero = 0;
+    const int32_t r32 = R, c32 = C;
+    int32_t len = 0;
+    // the early-out is answered on the host: recognised by the sentinel being overwritten
+    std::vector<double> host(2 * (size_t)std::max(C, 1), std::nan(""));
+    std::lock_guard<std::mutex> lock(g_mu);
+    const int rc = laplace_batch_locked(1, A, &zero, &r32, &c32, rows, &zero, cols, &zero,
+                                        host.data(), &zero, &len, part, nparts, device, d_out);
+    if (rc)
+        return rc;
+    *out_len = len;
+    trivial[0] = host[0]; // NaN unless the problem was the reference's early-out
+    trivial[1] = host[1];
     return PQ_OK;
 }
 

@@ -81,6 +81,13 @@ cudaError_t launch_laplace_reduce(const LapParams &P, int ncp1, cudaStream_t str
     return cudaGetLastError();
 }
 
+cudaError_t launch_laplace_scatter(const double2 *res, const int *map, int ncols, double2 *out,
+                                   cudaStream_t stream)
+{
+    laplace_scatter_kernel<<<(ncols + 127) / 128, 128, 0, stream>>>(res, map, ncols, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_sampler_pmf(const LapParams &P, int ncp1, const double2 *U, int d,
                                double *pmf, cudaStream_t stream)
 {

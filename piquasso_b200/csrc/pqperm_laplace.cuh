@@ -629,6 +629,18 @@ static __global__ void __launch_bounds__(128) laplace_reduce_kernel(const LapPar
     }
 }
 
+// out[j] = result of compact column map[j] of problem 0 (map[j] = NCP selects the full
+// product: a caller's zero-multiplicity column): the scatter the host does after a
+// download, for results that are to stay on the device.
+static __global__ void __launch_bounds__(128) laplace_scatter_kernel(const double2 *res,
+                                                                     const int *map, int ncols,
+                                                                     double2 *out)
+{
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    if (j < ncols)
+        out[j] = res[map[j]];
+}
+
 // Sampler epilogue (piquasso/_simulators/passive/sampling.py:736-747 of the
 // reference): pmf[m] = | sum_j in_j * partial_j * U[m, nz_j] |^2 for the d output
 // modes, from the Laplace results still in device memory.  One CTA per problem.

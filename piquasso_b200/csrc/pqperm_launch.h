@@ -43,6 +43,9 @@ namespace pqperm {
 cudaError_t launch_laplace(int S, int NCL, bool unitcols, int mode, const LapParams &P,
                            int total_blocks, size_t smem, cudaStream_t stream);
 cudaError_t launch_laplace_reduce(const LapParams &P, int ncp1, cudaStream_t stream);
+// out[j] = res[map[j]] for j < ncols (all device pointers)
+cudaError_t launch_laplace_scatter(const double2 *res, const int *map, int ncols, double2 *out,
+                                   cudaStream_t stream);
 // pmf rows of the Clifford-Clifford sampler from the Laplace results of P (device)
 cudaError_t launch_sampler_pmf(const LapParams &P, int ncp1, const double2 *U, int d,
                                double *pmf, cudaStream_t stream);

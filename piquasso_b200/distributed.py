@@ -138,6 +138,33 @@ def permanent_laplace_allgather(matrix, rows, cols, group=None, device_index=Non
         if device_index is None:
             device_index = torch.cuda.current_device()
         _lib.check(_lib.load().pq_set_devices((ctypes.c_int32 * 1)(device_index), 1))
+    import os
+    if (world > 1 and torch.cuda.is_available() and dist.get_backend(group) == "nccl"
+            and not os.environ.get("PQ_LAPLACE_ALLGATHER_HOST")):
+        # device end to end: the walk leaves its k complex partial sums in this rank's
+        # HBM, NCCL gathers them there, the ranks add them there in rank order, and ONE
+        # download brings the result home
+        lib = _lib.load()
+        local = torch.empty(2 * max(a.shape[1], 1), dtype=torch.float64,
+                            device="cuda:%d" % device_index)  # every column is written
+        triv = np.zeros(2)
+        out_len = ctypes.c_int(0)
+        rc = lib.pq_perm_laplace_partial_dev_c128(
+            a.ctypes.data_as(_lib.c_double_p), a.shape[0], a.shape[1],
+            r.ctypes.data_as(_lib.c_int32_p), c.ctypes.data_as(_lib.c_int32_p), rank, world,
+            device_index, ctypes.c_void_p(local.data_ptr()),
+            triv.ctypes.data_as(_lib.c_double_p), ctypes.byref(out_len))
+        _raise(rc)
+        if not np.isnan(triv[0]):  # the reference's early-out [1]: identical on all ranks
+            return np.array([1.0 + 0.0j])
+        local = local[: 2 * out_len.value]
+        gathered = torch.empty(world * local.numel(), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(gathered, local.contiguous(), group=group)
+        parts = gathered.view(world, -1)
+        total = parts[0] + parts[1]
+        for g in range(2, world):  # fixed order: every rank adds the same numbers the same way
+            total = total + parts[g]
+        return total.cpu().numpy().view(np.complex128).copy()
     mine = _laplace_device_partial(a, r, c, rank, world)
     if world == 1:
         return mine

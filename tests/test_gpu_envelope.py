@@ -308,3 +308,45 @@ def test_permanent_and_sampler_from_concurrent_threads(lib):
         t.join(timeout=120)
     assert not any(t.is_alive() for t in threads), "deadlock"
     assert not errors, errors
+
+
+def test_laplace_partials_left_on_the_device_sum_to_the_whole(lib):
+    """pq_perm_laplace_partial_dev_c128: the rank shares of one large permanent_laplace
+    stay in device memory (what permanent_laplace_allgather hands to NCCL); their sum
+    is the single call's result, zero-multiplicity columns and the early-out included."""
+    import torch
+    from piquasso_b200._math.permanent import permanent_laplace
+    rng = np.random.default_rng(11)
+    k = 18
+    a = np.ascontiguousarray(haar(k + 2, 3)[: k - 1, :k], dtype=np.complex128)
+    cases = [(np.ones(k - 1, np.int32), np.ones(k, np.int32))]
+    cols0 = np.ones(k, np.int32)
+    cols0[[2, 9]] = 0
+    rows0 = np.ones(k - 1, np.int32)
+    rows0[:2] = 0
+    cases.append((rows0, cols0))
+    for rows, cols in cases:
+        want = permanent_laplace(a, rows, cols)
+        total = torch.zeros(2 * k, dtype=torch.float64, device="cuda:0")
+        for part in range(3):
+            out = torch.zeros(2 * k, dtype=torch.float64, device="cuda:0")
+            triv = np.zeros(2)
+            n = ctypes.c_int(0)
+            _lib.check(lib.pq_perm_laplace_partial_dev_c128(
+                a.ctypes.data_as(_lib.c_double_p), k - 1, k,
+                rows.ctypes.data_as(_lib.c_int32_p), cols.ctypes.data_as(_lib.c_int32_p),
+                part, 3, 0, ctypes.c_void_p(out.data_ptr()),
+                triv.ctypes.data_as(_lib.c_double_p), ctypes.byref(n)))
+            assert n.value == k and np.isnan(triv[0])
+            total += out
+        got = total.cpu().numpy().view(np.complex128)
+        assert np.allclose(got, want, rtol=1e-12, atol=0)
+    out = torch.zeros(2 * k, dtype=torch.float64, device="cuda:0")
+    triv = np.zeros(2)
+    n = ctypes.c_int(0)
+    _lib.check(lib.pq_perm_laplace_partial_dev_c128(
+        a.ctypes.data_as(_lib.c_double_p), k - 1, k,
+        np.zeros(k - 1, np.int32).ctypes.data_as(_lib.c_int32_p),
+        np.ones(k, np.int32).ctypes.data_as(_lib.c_int32_p), 0, 3, 0,
+        ctypes.c_void_p(out.data_ptr()), triv.ctypes.data_as(_lib.c_double_p), ctypes.byref(n)))
+    assert n.value == 1 and triv[0] == 1.0 and triv[1] == 0.0

@@ -45,6 +45,33 @@ for k in (16, 29):
     t = time.perf_counter(); want = permanent_laplace(A, r, c); dt1 = time.perf_counter() - t
     e = float(np.max(np.abs(got - want) / np.abs(want))); ok &= e < 1e-11
     if rank == 0: print(f"laplace k={k} world={world}: {dt*1e3:.2f} ms vs {dt1*1e3:.2f} ms on one GPU, max relerr {e:.2e}", flush=True)
+# latency of the exchange: results left on the device vs staged through the host
+for k in (12, 16, 20, 24):
+    A = np.ascontiguousarray(unitary_group.rvs(k + 3, random_state=k)[: k - 1, :k])
+    r = np.ones(k - 1, np.int32); c = np.ones(k, np.int32)
+    res = {}
+    for mode in ("device", "host"):
+        if mode == "host":
+            os.environ["PQ_LAPLACE_ALLGATHER_HOST"] = "1"
+        else:
+            os.environ.pop("PQ_LAPLACE_ALLGATHER_HOST", None)
+        for _ in range(5):
+            permanent_laplace_allgather(A, r, c, device_index=local)
+        ts = []
+        for _ in range(30):
+            dist.barrier(); torch.cuda.synchronize(); t = time.perf_counter()
+            permanent_laplace_allgather(A, r, c, device_index=local)
+            ts.append(time.perf_counter() - t)
+        res[mode] = float(np.median(ts)) * 1e3
+    os.environ.pop("PQ_LAPLACE_ALLGATHER_HOST", None)
+    if rank == 0: print(f"laplace k={k} world={world}: device path {res['device']:.3f} ms, host-staged {res['host']:.3f} ms", flush=True)
+# zero-multiplicity column (gets the full product) and the reference's early-out
+A = np.ascontiguousarray(unitary_group.rvs(12, random_state=5)[:9, :11])
+r = np.ones(9, np.int32); c = np.array([1, 1, 0, 1, 1, 1, 1, 1, 1, 1, 1], np.int32)
+got = permanent_laplace_allgather(A, r, c, device_index=local); want = permanent_laplace(A, r, c)
+ok &= bool(np.allclose(got, want, rtol=1e-11, atol=0))
+got = permanent_laplace_allgather(A, np.zeros(9, np.int32), c, device_index=local)
+ok &= got.shape == (1,) and got[0] == 1
 if rank == 0: print(f"ALL OK (incl. laplace) = {ok}", flush=True)
 dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if ok else 1)
