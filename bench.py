@@ -399,9 +399,10 @@ def main_arm(args):
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
                                   "perm_walk_binary_pm<40,3,64> launch, ncu --set full, "
                                   "profiles/" + os.path.basename(TRAFFIC_NCU_CSV),
-                "peak_source": "measured in this run on rank 0's GPU: dependent-free DFMA loop, "
-                               "2 flop per FMA (pq_fp64_peak_tflops); MEASURED_PEAKS.json holds "
-                               "no FP64 figure",
+                "peak_source": "measured in this run on rank 0's GPU: 16 independent DFMA "
+                               "chains per thread with distinct operands, 2 flop per FMA "
+                               "(pq_fp64_peak_tflops; 62-63 of the 64 FMA/clk/SM); "
+                               "MEASURED_PEAKS.json holds no FP64 figure",
                 "nominal_peak": NOMINAL_FP64_TFLOPS,
                 "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
                 "kernel_ms": kernel_ms,

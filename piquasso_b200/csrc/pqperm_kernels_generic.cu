@@ -52,33 +52,46 @@ cudaError_t launch_generic(int ncp, bool binary, bool unitcols, const WalkParams
 }
 
 // ---- DFMA probe: the FP64 roofline denominator, measured -------------------
-// 8 independent FMA chains per thread, no memory traffic.
-__global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, double *sink)
+// 16 independent FMA chains per thread, every instruction with three distinct
+// register operands, no memory traffic: 62-63 of the 64 FMA/clk/SM on B200
+// (tools/dfma_operands.cu; a loop whose chains share two operands, as round 1 used,
+// stops at 56-58 -- the denominator must be the best the pipe can do).
+__global__ void __launch_bounds__(64) dfma_probe_kernel(int iters, double *sink,
+                                                        const double *in)
 {
-    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
-    double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
-    const double m = 1.0 - 1e-12, c = 1e-13;
-    for (int i = 0; i < iters; i++) {
-        a0 = __fma_rn(a0, m, c);
-        a1 = __fma_rn(a1, m, c);
-        a2 = __fma_rn(a2, m, c);
-        a3 = __fma_rn(a3, m, c);
-        a4 = __fma_rn(a4, m, c);
-        a5 = __fma_rn(a5, m, c);
-        a6 = __fma_rn(a6, m, c);
-        a7 = __fma_rn(a7, m, c);
+    double x[16], y[16], z[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        x[i] = in[i];
+        y[i] = in[16 + i] + threadIdx.x * 1e-12; // per-thread: stays in vector registers
+        z[i] = in[32 + i];
     }
-    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            x[i] = __fma_rn(y[i], z[i], x[i]);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        s += x[i];
     if (s == 12345.678)
         sink[0] = s;
 }
 
+// `sink` must hold 64 doubles: [0] is the never-taken output, [8..56) the operands.
 cudaError_t launch_dfma_probe(int num_sms, int iters, double *sink, cudaStream_t stream,
                               double *flops)
 {
-    const int grid = num_sms * 8;
-    dfma_probe_kernel<<<grid, 256, 0, stream>>>(iters, sink);
-    *flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)grid;
+    static double h_in[48];
+    for (int i = 0; i < 48; i++)
+        h_in[i] = 1.0 + 1e-9 * i;
+    cudaError_t e = cudaMemcpyAsync(sink + 8, h_in, sizeof(h_in), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess)
+        return e;
+    const int grid = num_sms * 8; // 8 CTAs of 64 threads per SM: 16 warps
+    dfma_probe_kernel<<<grid, 64, 0, stream>>>(iters, sink, sink + 8);
+    *flops = 2.0 * 16.0 * (double)iters * 64.0 * (double)grid;
     return cudaGetLastError();
 }
 
