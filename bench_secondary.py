@@ -203,7 +203,8 @@ def run(lib, peak_tflops, rank, world, local_rank, with_reference, sampler_shots
     sampling.TIMERS.clear()
     lib.pq_sampler_work_reset()
     t0 = time.perf_counter()
-    samples = generate_samples_sharded(inp, sampler_shots, u100, 123, device_index=dev)
+    samples = generate_samples_sharded(inp, sampler_shots, u100, 123, device_index=dev,
+                                       as_array=True)
     dt = time.perf_counter() - t0
     work = (ctypes.c_double * 2)()
     lib.pq_sampler_work(work)
@@ -231,14 +232,15 @@ def run(lib, peak_tflops, rank, world, local_rank, with_reference, sampler_shots
                       "frac": flops / world / ksec / 1e12 / peak_tflops if ksec > 0 and peak_tflops > 0 else None,
                       "note": "per GPU: 22k flops per Gray-code term of a k-column Laplace problem "
                               "(SURVEY.md 8d) over the slowest rank's kernel seconds"},
-         "first_sample": list(samples[0])}
+         "output": "samples returned as one (shots, modes) int32 array on every rank",
+         "first_sample": [int(x) for x in samples[0]]}
     if oracle is not None:
         t0 = time.perf_counter()
         s0, tl = reference_shot(u100, inp, 123, oracle.ref_permanent_laplace)
         rt = time.perf_counter() - t0
         e["reference"] = {"kind": "reference", "cores": os.cpu_count(), "seconds_per_shot": rt,
                           "seconds_per_shot_in_permanent_laplace": tl, "same_config": True,
-                          "first_shot_identical": s0 == samples[0],
+                          "first_shot_identical": s0 == tuple(int(x) for x in samples[0]),
                           "speedup_per_shot": rt / (dt / sampler_shots)}
     out["cfg4_sampler_100modes_25photons"] = e
     return out

@@ -182,7 +182,7 @@ def permanent_laplace_allgather(matrix, rows, cols, group=None, device_index=Non
 
 def generate_samples_sharded(input, shots, interferometer, seed_sequence,
                              reject_condition=None, group=None, pmf_rows=None,
-                             device_index=None):
+                             device_index=None, as_array=False):
     """The lock-step sampler with the SHOTS sharded over the ranks of ``group``.
 
     Shots are independent (shot ``idx`` owns ``default_rng(seed_sequence + idx)``),
@@ -190,6 +190,10 @@ def generate_samples_sharded(input, shots, interferometer, seed_sequence,
     GPU; there is no exchange step on the data path, only one all-gather of the
     finished samples at the end.  Every rank returns the full list, identical to
     the single-GPU (and to the reference's) result.
+
+    ``as_array`` returns the samples as one (shots, d) int32 array instead of the
+    reference's list of tuples (10^4 tuples of 100 Python ints take 20 ms to build --
+    a tenth of an 8-GPU run).
 
     ``device_index`` is the CUDA device this rank's shots run on; the default is
     the rank's current torch device (``torch.cuda.current_device()``), i.e. what
@@ -239,4 +243,4 @@ def generate_samples_sharded(input, shots, interferometer, seed_sequence,
         g = gathered.cpu().numpy().reshape(world, per, d)
         mine = np.concatenate([g[r, : (shots * (r + 1)) // world - (shots * r) // world]
                                for r in range(world)], axis=0)
-    return [tuple(row) for row in mine.tolist()]
+    return mine if as_array else [tuple(row) for row in mine.tolist()]

@@ -350,3 +350,39 @@ def test_laplace_partials_left_on_the_device_sum_to_the_whole(lib):
         np.ones(k, np.int32).ctypes.data_as(_lib.c_int32_p), 0, 3, 0,
         ctypes.c_void_p(out.data_ptr()), triv.ctypes.data_as(_lib.c_double_p), ctypes.byref(n)))
     assert n.value == 1 and triv[0] == 1.0 and triv[1] == 0.0
+
+
+def test_round2_abi_entries(lib):
+    """pq_set_timing, pq_sampler_work / _detail and the explicit-device pmf entry."""
+    from piquasso_b200.sampling import sampler_pmf
+    u = haar(16, 16)
+    want = complex(permanent(u, _ones(16), _ones(16)))
+    assert lib.pq_last_kernel_ms(0) > 0.0
+    try:
+        lib.pq_set_timing(0)
+        assert complex(permanent(u, _ones(16), _ones(16))) == want   # same launch, same bits
+        assert lib.pq_last_kernel_ms(0) == -1.0
+    finally:
+        lib.pq_set_timing(1)
+    assert complex(permanent(u, _ones(16), _ones(16))) == want
+    assert lib.pq_last_kernel_ms(0) > 0.0
+    # sampler work counters: 3 shots with 4 photons placed and a 5th input photon chosen:
+    # Laplace problems of 5 columns and 3 binary digits = 8 Gray-code terms each
+    d = 9
+    U = haar(d, 4)
+    out_occ = np.zeros((3, d), np.int32)
+    in_occ = np.zeros((3, d), np.int32)
+    out_occ[:, [0, 2, 5, 7]] = 1
+    in_occ[:, :5] = 1
+    lib.pq_sampler_work_reset()
+    rows = sampler_pmf(U, out_occ, in_occ)
+    rows_dev = sampler_pmf(U, out_occ, in_occ, device=0)
+    assert np.array_equal(rows, rows_dev)
+    work = (ctypes.c_double * 2)()
+    lib.pq_sampler_work(work)
+    assert work[0] == 2 * 3 * 8 and work[1] == 2 * 3 * 8 * 22 * 5
+    detail = (ctypes.c_double * 8)()
+    lib.pq_last_sampler_detail(detail)
+    assert all(x >= 0.0 for x in detail) and detail[3] > 0.0
+    from conftest import oracle_pmf_rows
+    assert np.allclose(rows, oracle_pmf_rows(U, out_occ, in_occ), rtol=1e-10, atol=1e-16)
