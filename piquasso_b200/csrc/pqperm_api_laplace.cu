@@ -239,7 +239,17 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
     const int NCP = bk.S * bk.NCL, ncp1 = NCP + 1;
     const int groups_per_block = kLapThreads / bk.S;
     const long long wave = (long long)c->num_sms * 8;
-    const long long budget = std::max<long long>(1, (4 * wave) / n);
+    // CTAs per problem: enough of them for ~32 waves over the whole launch.  Problems of
+    // one photon step differ in size by factors of 2-4 (output collisions), and CTAs are
+    // dispatched in problem order: fine-grained slices even the tail out (B200, 10^4 shots:
+    // kernels 1.36 s at 4 waves, 1.28 s at 32; 1250 shots: 0.176 -> 0.162 s).  Tuning
+    // knob: PQ_LAP_WAVES.
+    static const long long kWaves = [] {
+        const char *e = std::getenv("PQ_LAP_WAVES");
+        const long long v = e ? std::atoll(e) : 32;
+        return std::max<long long>(1, std::min<long long>(v, 64));
+    }();
+    const long long budget = std::max<long long>(1, (kWaves * wave) / n);
     int total_blocks = 0;
     for (LapProblem &q : bk.probs) {
         long long nb = (q.nseg + groups_per_block - 1) / groups_per_block;
@@ -737,10 +747,10 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
         // with growing column counts, and regrowing pinned / device buffers step
         // after step (free + allocate, megabytes each) is what the device phase was
         // losing milliseconds to.  Bounds: NCP + 1 <= min(d, 64) + 1 columns per
-        // result, at most 4 waves + one CTA per shot.
+        // result, at most 64 waves (the cap of PQ_LAP_WAVES) + one CTA per shot.
         const size_t ns = (size_t)nshots;
         const size_t ncp1_max = (size_t)std::min(d, (int)kMaxCols) + 1;
-        const size_t blocks_max = (size_t)4 * c->num_sms * 8 + ns;
+        const size_t blocks_max = (size_t)64 * c->num_sms * 8 + ns;
         if ((rc = grow_dev(c, 0, sizeof(LapProblem) * ns)) ||
             (rc = grow_host(c, 4, sizeof(LapProblem) * ns)) ||
             (rc = grow_dev(c, 2, blocks_max * ncp1_max * 4 * sizeof(double))) ||
