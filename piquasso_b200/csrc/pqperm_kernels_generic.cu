@@ -51,6 +51,13 @@ cudaError_t launch_generic(int ncp, bool binary, bool unitcols, const WalkParams
     }
 }
 
+#ifdef PQ_TRACE
+extern "C" int pq_debug_trace_read(unsigned long long *out, int n)
+{
+    return (int)cudaMemcpyFromSymbol(out, pq_trace_buf, (size_t)n * 8);
+}
+#endif
+
 // ---- DFMA probe: the FP64 roofline denominator, measured -------------------
 // 16 independent FMA chains per thread, every instruction with three distinct
 // register operands, no memory traffic: 62-63 of the 64 FMA/clk/SM on B200

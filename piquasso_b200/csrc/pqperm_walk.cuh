@@ -24,6 +24,23 @@
 
 namespace pqperm {
 
+#ifdef PQ_TRACE
+// Experiment builds only (tools/trace_small.py): thread 0 of every CTA stamps
+// %globaltimer at the phase boundaries of the generic walk.
+static __device__ unsigned long long pq_trace_buf[8 * 8192];
+__device__ __forceinline__ void trace_stamp(int phase)
+{
+    if (threadIdx.x == 0 && blockIdx.x < 8192) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        pq_trace_buf[blockIdx.x * 8 + phase] = t;
+    }
+}
+#define PQ_STAMP(p) trace_stamp(p)
+#else
+#define PQ_STAMP(p)
+#endif
+
 // ---- dynamic segment distribution -------------------------------------------
 // The warp schedulers do not share issue slots fairly between resident warps:
 // with a static split the favoured warp of each SM sub-partition finishes at
@@ -279,11 +296,13 @@ __device__ __forceinline__ void generic_walk_body(const WalkParams &P, const dou
     __shared__ double s_wtab[BINARY ? 1 : kMaxSegLenNary];
     __shared__ uint8_t s_sched[BINARY ? 1 : kMaxSegLenNary];
     const int W = (int)P.W;
+    PQ_STAMP(0);
     {
         const int nelem = (P.D + 1) * NC;
         for (int i = threadIdx.x; i < nelem; i += NT)
             smA[i] = src[i];
         __syncthreads();
+        PQ_STAMP(1);
         build_lowtab<NC, BINARY, NT>(P, smA, smA + (P.D + 1) * NC);
         if (!BINARY) {
             for (int m = threadIdx.x; m < W; m += NT) {
@@ -303,6 +322,10 @@ __device__ __forceinline__ void generic_walk_body(const WalkParams &P, const dou
         }
     }
     __syncthreads();
+    PQ_STAMP(2);
+#ifdef PQ_TRACE
+    bool trace_first = true;
+#endif
 
     dd totre{0.0, 0.0}, totim{0.0, 0.0};
     int round = 0;
@@ -324,6 +347,12 @@ __device__ __forceinline__ void generic_walk_body(const WalkParams &P, const dou
                                       factor);
         if (!valid)
             factor = 0.0;
+#ifdef PQ_TRACE
+        if (trace_first) {
+            PQ_STAMP(3);
+            trace_first = false;
+        }
+#endif
 
         dd segre{0.0, 0.0}, segim{0.0, 0.0};
         constexpr int CHUNK = 64;
@@ -370,7 +399,9 @@ __device__ __forceinline__ void generic_walk_body(const WalkParams &P, const dou
         dd_add(totre, segre);
         dd_add(totim, segim);
     }
+    PQ_STAMP(4);
     finish_grid<NT>(P, totre, totim);
+    PQ_STAMP(5);
 }
 
 template <int NC, bool BINARY, bool UNITCOLS, int NT>
