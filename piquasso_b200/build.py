@@ -52,6 +52,10 @@ def _units():
         for mode in (0, 1, 2):
             units.append(("laplace_u%d_m%d" % (unit, mode), "pqperm_kernels_laplace.cu",
                           ["-DPQ_LAP_UNIT=%d" % unit, "-DPQ_LAP_MODE=%d" % mode]))
+        # batched permanents: one lane per segment for 9..20 / 21..32 columns
+        for part in (1, 2):
+            units.append(("laplace_u%d_m2_p%d" % (unit, part), "pqperm_kernels_laplace.cu",
+                          ["-DPQ_LAP_UNIT=%d" % unit, "-DPQ_LAP_MODE=2", "-DPQ_LAP_PART=%d" % part]))
     for part, lo, hi in BINARY_PARTS:
         units.append((
             "binary%d" % part, "pqperm_kernels_binary.cu",

@@ -137,7 +137,10 @@ int lap_shape(int R, int C, const int32_t *rows, const int32_t *cols, LapShape &
 // Fills the walk parameters of a described problem: digits 0..q-1 are walked
 // inside a segment of W <= kLapSegLen terms, the rest index the segments.
 // Problems wider than kMaxCols keep their column tables in `wide`.
-void lap_fill(const LapShape &sh, int ncp, LapProblem &q, LapWide *wide = nullptr)
+// min_segs > 1 (batched permanents): small problems are cut into shorter segments
+// so that they still yield that many of them -- a CTA's threads each take one.
+void lap_fill(const LapShape &sh, int ncp, LapProblem &q, LapWide *wide = nullptr,
+              int min_segs = 1)
 {
     std::memset(&q, 0, sizeof(q));
     q.D = sh.D;
@@ -148,7 +151,8 @@ void lap_fill(const LapShape &sh, int ncp, LapProblem &q, LapWide *wide = nullpt
     int qd = 0;
     long long W = 1;
     for (int d = 0; d < sh.D; d++) {
-        if (qd == d && qd < kMaxLowDigits && W * (sh.mult[d] + 1) <= seglen) {
+        if (qd == d && qd < kMaxLowDigits && W * (sh.mult[d] + 1) <= seglen &&
+            (min_segs <= 1 || total / (W * (sh.mult[d] + 1)) >= min_segs)) {
             W *= (sh.mult[d] + 1);
             qd++;
         }
@@ -189,14 +193,14 @@ struct Bucket {
     bool need_full = false;   // some problem has a zero-multiplicity column (it gets the full product)
 };
 
-// buckets[(S index) * 17 * 2 + NCL * 2 + unit]
+// buckets[(S index) * 33 * 2 + NCL * 2 + unit]
 struct Buckets {
     std::vector<Bucket> b;
-    Buckets() : b(4 * 17 * 2) {}
+    Buckets() : b(4 * 33 * 2) {}
     Bucket &get(const LapVariant &v, bool unit)
     {
         const int si = v.S == 1 ? 0 : (v.S == 2 ? 1 : (v.S == 4 ? 2 : 3));
-        Bucket &k = b[(si * 17 + v.NCL) * 2 + (unit ? 1 : 0)];
+        Bucket &k = b[(si * 33 + v.NCL) * 2 + (unit ? 1 : 0)];
         k.S = v.S;
         k.NCL = v.NCL;
         k.unit = unit;
@@ -216,6 +220,74 @@ struct Buckets {
 // per calling thread (the sampler step plans outside the library lock); keeps its
 // capacity between calls
 thread_local Buckets g_buckets;
+
+// One planner thread's share of a batch.
+struct PlanPart {
+    Buckets buckets;
+    int rc = PQ_OK;
+    std::string err;
+    bool any = false;
+};
+
+// Plans problems [0, n) into g_buckets: plan_range(begin, end, buckets, part) fills
+// `buckets` for its range.  With thousands of problems the range is cut over a few
+// host threads (PQ_PLAN_THREADS caps them, 1 = the calling thread), each filling its
+// own buckets, merged in index order.
+template <typename F>
+int plan_parallel(int n, F &plan_range, bool &any)
+{
+    g_buckets.reset();
+    any = false;
+    static const int thread_cap = [] {
+        const char *env = std::getenv("PQ_PLAN_THREADS");
+        const int v = env ? std::atoi(env) : kPlanThreadsMax;
+        return std::max(1, std::min(v, 64));
+    }();
+    const int nthreads = (int)std::min<long long>(
+        {(long long)thread_cap, (long long)n / kPlanShotsPerThread,
+         (long long)std::max(1u, std::thread::hardware_concurrency())});
+    if (nthreads <= 1) {
+        PlanPart part;
+        plan_range(0, n, g_buckets, part);
+        if (part.rc)
+            return fail(part.rc, part.err);
+        any = part.any;
+        return PQ_OK;
+    }
+    static thread_local std::vector<PlanPart> parts; // keeps the buckets' capacity
+    if ((int)parts.size() < nthreads)
+        parts.resize(nthreads);
+    std::vector<std::thread> workers;
+    for (int t = 0; t < nthreads; t++) {
+        parts[t].buckets.reset();
+        parts[t].rc = PQ_OK;
+        parts[t].any = false;
+        const int begin = (int)((long long)n * t / nthreads);
+        const int end = (int)((long long)n * (t + 1) / nthreads);
+        workers.emplace_back(std::ref(plan_range), begin, end, std::ref(parts[t].buckets),
+                             std::ref(parts[t]));
+    }
+    for (std::thread &w : workers)
+        w.join();
+    for (int t = 0; t < nthreads; t++) {
+        if (parts[t].rc)
+            return fail(parts[t].rc, parts[t].err);
+        any = any || parts[t].any;
+        for (size_t i = 0; i < parts[t].buckets.b.size(); i++) {
+            const Bucket &src = parts[t].buckets.b[i];
+            if (src.probs.empty())
+                continue;
+            Bucket &dst = g_buckets.b[i];
+            dst.S = src.S;
+            dst.NCL = src.NCL;
+            dst.unit = src.unit;
+            dst.max_D = std::max(dst.max_D, src.max_D);
+            dst.probs.insert(dst.probs.end(), src.probs.begin(), src.probs.end());
+            dst.wide.insert(dst.wide.end(), src.wide.begin(), src.wide.end());
+        }
+    }
+    return PQ_OK;
+}
 
 struct Epilogue {
     const double2 *d_U = nullptr; // gather mode / sampler: matrix on the device
@@ -301,7 +373,7 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
     P.nprob = n;
     P.perm_only = (epi && epi->perm_only) ? 1 : 0;
     P.max_D = bk.max_D;
-    const size_t smem = lap_smem_bytes(bk.max_D, bk.S, bk.NCL);
+    const size_t smem = lap_smem_bytes(bk.max_D, bk.S, bk.NCL, P.perm_only != 0);
     PQ_CUDA(cudaEventRecord(c->lap_ev0, st));
     // accumulation mode of the walk: full product only (batched permanents), the
     // leave-one-out sums, or both (a caller's zero-multiplicity column gets the full product)
@@ -592,12 +664,7 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
     g_sampler_profile[0] = g_sampler_profile[1] = g_sampler_profile[2] = g_sampler_profile[3] = 0.0;
     // Shots are planned independently: with thousands of them the range is cut
     // over a few host threads, each filling its own buckets, merged in shot order.
-    struct Part {
-        Buckets buckets;
-        int rc = PQ_OK;
-        std::string err;
-        bool any = false;
-    };
+    using Part = PlanPart;
     auto plan_range = [&](int begin, int end, Buckets &buckets, Part &part) {
         std::vector<double> trivial_row(pmf ? 0 : d);
         LapShape sh;
@@ -653,57 +720,9 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
         }
     };
     int rc = PQ_OK;
-    g_buckets.reset();
     bool any = false;
-    // PQ_PLAN_THREADS caps the planner threads (1 = plan on the calling thread)
-    static const int thread_cap = [] {
-        const char *env = std::getenv("PQ_PLAN_THREADS");
-        const int v = env ? std::atoi(env) : kPlanThreadsMax;
-        return std::max(1, std::min(v, 64));
-    }();
-    const int nthreads = (int)std::min<long long>(
-        {(long long)thread_cap, (long long)nshots / kPlanShotsPerThread,
-         (long long)std::max(1u, std::thread::hardware_concurrency())});
-    if (nthreads <= 1) {
-        Part part;
-        plan_range(0, nshots, g_buckets, part);
-        if (part.rc)
-            return fail(part.rc, part.err);
-        any = part.any;
-    } else {
-        static thread_local std::vector<Part> parts; // keeps the buckets' capacity
-        if ((int)parts.size() < nthreads)
-            parts.resize(nthreads);
-        std::vector<std::thread> workers;
-        for (int t = 0; t < nthreads; t++) {
-            parts[t].buckets.reset();
-            parts[t].rc = PQ_OK;
-            parts[t].any = false;
-            const int begin = (int)((long long)nshots * t / nthreads);
-            const int end = (int)((long long)nshots * (t + 1) / nthreads);
-            workers.emplace_back(plan_range, begin, end, std::ref(parts[t].buckets),
-                                 std::ref(parts[t]));
-        }
-        for (std::thread &w : workers)
-            w.join();
-        for (int t = 0; t < nthreads; t++) {
-            if (parts[t].rc)
-                return fail(parts[t].rc, parts[t].err);
-            any = any || parts[t].any;
-            for (size_t i = 0; i < parts[t].buckets.b.size(); i++) {
-                const Bucket &src = parts[t].buckets.b[i];
-                if (src.probs.empty())
-                    continue;
-                Bucket &dst = g_buckets.b[i];
-                dst.S = src.S;
-                dst.NCL = src.NCL;
-                dst.unit = src.unit;
-                dst.max_D = std::max(dst.max_D, src.max_D);
-                dst.probs.insert(dst.probs.end(), src.probs.begin(), src.probs.end());
-                dst.wide.insert(dst.wide.end(), src.wide.begin(), src.wide.end());
-            }
-        }
-    }
+    if ((rc = plan_parallel(nshots, plan_range, any)))
+        return rc;
     g_sampler_profile[0] = ms_since(t_begin);
     {
         double terms = 0.0, flops = 0.0;
@@ -803,45 +822,57 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
 int perm_batch_locked(const double *U, int R, int C, int nprob, const int32_t *row_mult,
                       const int32_t *col_mult, double *out)
 {
-    std::string err;
-    LapShape sh;
-    g_buckets.reset();
-    bool any = false;
-    for (int b = 0; b < nprob; b++) {
-        const int32_t *rw = row_mult + (size_t)b * R, *cl = col_mult + (size_t)b * C;
-        int rc = lap_shape(R, C, rw, cl, sh, err);
-        if (rc)
-            return fail(rc, err);
-        long long sr = 0, sc = 0;
-        for (int i = 0; i < R; i++)
-            sr += rw[i];
-        for (int j = 0; j < C; j++)
-            sc += cl[j];
-        if (sr != sc) // src/permanent.cpp:97-104
-            return fail(PQ_ERR_SUM_MISMATCH,
-                        "Number of input and output states should be equal (problem " +
-                            std::to_string(b) + ")");
-        if (sh.trivial) { // src/permanent.cpp:106-108
-            out[2 * (size_t)b] = 1.0;
-            out[2 * (size_t)b + 1] = 0.0;
-            continue;
+    auto plan_range = [&](int begin, int end, Buckets &buckets, PlanPart &part) {
+        LapShape sh;
+        for (int b = begin; b < end; b++) {
+            const int32_t *rw = row_mult + (size_t)b * R, *cl = col_mult + (size_t)b * C;
+            part.rc = lap_shape(R, C, rw, cl, sh, part.err);
+            if (part.rc)
+                return;
+            long long sr = 0, sc = 0;
+            for (int i = 0; i < R; i++)
+                sr += rw[i];
+            for (int j = 0; j < C; j++)
+                sc += cl[j];
+            if (sr != sc) { // src/permanent.cpp:97-104
+                part.rc = PQ_ERR_SUM_MISMATCH;
+                part.err = "Number of input and output states should be equal (problem " +
+                           std::to_string(b) + ")";
+                return;
+            }
+            if (sh.trivial) { // src/permanent.cpp:106-108
+                out[2 * (size_t)b] = 1.0;
+                out[2 * (size_t)b + 1] = 0.0;
+                continue;
+            }
+            // full product only: one lane per segment up to kPermS1MaxCols columns
+            const LapVariant v = perm_variant(sh.NC);
+            Bucket &bk = buckets.get(v, sh.unit);
+            if (lap_smem_bytes(sh.D, v.S, v.NCL, true) > kLapSmemLimit) {
+                part.rc = PQ_ERR_TOO_LARGE;
+                part.err = kLapTooWide;
+                return;
+            }
+            LapProblem q;
+            LapWide w;
+            // small problems: short segments, so that a CTA's threads all get one
+            lap_fill(sh, v.S * v.NCL, q, v.S == 32 ? &w : nullptr, kLapThreads / v.S);
+            q.tag = b;
+            q.rowmode[0] = (uint16_t)sh.pinned;
+            for (int k = 0; k < sh.D; k++)
+                q.rowmode[k + 1] = (uint16_t)sh.src_row[k];
+            bk.max_D = std::max(bk.max_D, sh.D);
+            bk.probs.push_back(q);
+            if (v.S == 32)
+                bk.wide.push_back(w);
+            part.any = true;
         }
-        const LapVariant v = laplace_variant(sh.NC);
-        Bucket &bk = g_buckets.get(v, sh.unit);
-        if (lap_smem_bytes(sh.D, v.S, v.NCL) > kLapSmemLimit)
-            return fail(PQ_ERR_TOO_LARGE, kLapTooWide);
-        LapProblem q;
-        LapWide w;
-        lap_fill(sh, v.S * v.NCL, q, v.S == 32 ? &w : nullptr);
-        q.tag = b;
-        q.rowmode[0] = (uint16_t)sh.pinned;
-        for (int k = 0; k < sh.D; k++)
-            q.rowmode[k + 1] = (uint16_t)sh.src_row[k];
-        bk.max_D = std::max(bk.max_D, sh.D);
-        bk.probs.push_back(q);
-        if (v.S == 32)
-            bk.wide.push_back(w);
-        any = true;
+    };
+    bool any = false;
+    {
+        const int prc = plan_parallel(nprob, plan_range, any);
+        if (prc)
+            return prc;
     }
     if (!any)
         return PQ_OK;

@@ -11,9 +11,14 @@
 #if !defined(PQ_LAP_UNIT) || !defined(PQ_LAP_MODE)
 #error "PQ_LAP_UNIT and PQ_LAP_MODE must be defined"
 #endif
-#define PQ_CONCAT3_(a, b, c, d) a##b##c##d
-#define PQ_CONCAT3(a, b, c, d) PQ_CONCAT3_(a, b, c, d)
-#define PQ_LAP_LAUNCHER PQ_CONCAT3(launch_laplace_u, PQ_LAP_UNIT, _m, PQ_LAP_MODE)
+// -DPQ_LAP_PART=1, 2 (mode 2 only): the one-lane-per-segment instantiations of the
+// batched permanents for 9..20 and 21..32 columns, translation units of their own.
+#ifndef PQ_LAP_PART
+#define PQ_LAP_PART 0
+#endif
+#define PQ_CONCAT3_(a, b, c, d, e, f) a##b##c##d##e##f
+#define PQ_CONCAT3(a, b, c, d, e, f) PQ_CONCAT3_(a, b, c, d, e, f)
+#define PQ_LAP_LAUNCHER PQ_CONCAT3(launch_laplace_u, PQ_LAP_UNIT, _m, PQ_LAP_MODE, _p, PQ_LAP_PART)
 
 namespace pqperm {
 
@@ -47,6 +52,13 @@ cudaError_t PQ_LAP_LAUNCHER(
 #define PQ_CASE(SS, NN)                                                                 \
     if (S == SS && NCL == NN)                                                           \
         return launch_one<NN, SS>(P, total_blocks, smem, stream);
+#if PQ_LAP_PART == 1
+    PQ_CASE(1, 9) PQ_CASE(1, 10) PQ_CASE(1, 11) PQ_CASE(1, 12) PQ_CASE(1, 13) PQ_CASE(1, 14)
+    PQ_CASE(1, 15) PQ_CASE(1, 16) PQ_CASE(1, 17) PQ_CASE(1, 18) PQ_CASE(1, 19) PQ_CASE(1, 20)
+#elif PQ_LAP_PART == 2
+    PQ_CASE(1, 21) PQ_CASE(1, 22) PQ_CASE(1, 23) PQ_CASE(1, 24) PQ_CASE(1, 25) PQ_CASE(1, 26)
+    PQ_CASE(1, 27) PQ_CASE(1, 28) PQ_CASE(1, 29) PQ_CASE(1, 30) PQ_CASE(1, 31) PQ_CASE(1, 32)
+#else
     PQ_CASE(1, 1) PQ_CASE(1, 2) PQ_CASE(1, 3) PQ_CASE(1, 4) PQ_CASE(1, 5) PQ_CASE(1, 6)
     PQ_CASE(1, 7) PQ_CASE(1, 8)
     PQ_CASE(2, 5) PQ_CASE(2, 6) PQ_CASE(2, 7) PQ_CASE(2, 8) PQ_CASE(2, 9) PQ_CASE(2, 10) PQ_CASE(2, 11) PQ_CASE(2, 12)
@@ -54,23 +66,29 @@ cudaError_t PQ_LAP_LAUNCHER(
     PQ_CASE(4, 5) PQ_CASE(4, 6) PQ_CASE(4, 7) PQ_CASE(4, 8) PQ_CASE(4, 9) PQ_CASE(4, 10) PQ_CASE(4, 11) PQ_CASE(4, 12)
     PQ_CASE(4, 13) PQ_CASE(4, 14) PQ_CASE(4, 15) PQ_CASE(4, 16)
     PQ_CASE(32, 3) PQ_CASE(32, 4) PQ_CASE(32, 5) PQ_CASE(32, 6) PQ_CASE(32, 7) PQ_CASE(32, 8)
+#endif
 #undef PQ_CASE
     return cudaErrorInvalidValue;
 }
 
-#if PQ_LAP_UNIT == 1 && PQ_LAP_MODE == 0
-#define PQ_DECL(u, m)                                                                   \
-    cudaError_t launch_laplace_u##u##_m##m(int, int, const LapParams &, int, size_t, cudaStream_t);
-PQ_DECL(0, 0) PQ_DECL(0, 1) PQ_DECL(0, 2) PQ_DECL(1, 1) PQ_DECL(1, 2)
+#if PQ_LAP_UNIT == 1 && PQ_LAP_MODE == 0 && PQ_LAP_PART == 0
+#define PQ_DECL(u, m, p)                                                                \
+    cudaError_t launch_laplace_u##u##_m##m##_p##p(int, int, const LapParams &, int, size_t,  \
+                                                  cudaStream_t);
+PQ_DECL(0, 0, 0) PQ_DECL(0, 1, 0) PQ_DECL(0, 2, 0) PQ_DECL(1, 1, 0) PQ_DECL(1, 2, 0)
+PQ_DECL(0, 2, 1) PQ_DECL(0, 2, 2) PQ_DECL(1, 2, 1) PQ_DECL(1, 2, 2)
 #undef PQ_DECL
 
 cudaError_t launch_laplace(int S, int NCL, bool unitcols, int mode, const LapParams &P,
                            int total_blocks, size_t smem, cudaStream_t stream)
 {
-#define PQ_GO(u, m)                                                                     \
-    if ((unitcols ? 1 : 0) == u && mode == m)                                           \
-        return launch_laplace_u##u##_m##m(S, NCL, P, total_blocks, smem, stream);
-    PQ_GO(0, 0) PQ_GO(0, 1) PQ_GO(0, 2) PQ_GO(1, 0) PQ_GO(1, 1) PQ_GO(1, 2)
+    // batched permanents, one lane per segment, more than 8 columns (perm_variant)
+    const int part = (mode == 2 && S == 1 && NCL > 8) ? (NCL <= 20 ? 1 : 2) : 0;
+#define PQ_GO(u, m, p)                                                                  \
+    if ((unitcols ? 1 : 0) == u && mode == m && part == p)                              \
+        return launch_laplace_u##u##_m##m##_p##p(S, NCL, P, total_blocks, smem, stream);
+    PQ_GO(0, 0, 0) PQ_GO(0, 1, 0) PQ_GO(0, 2, 0) PQ_GO(1, 0, 0) PQ_GO(1, 1, 0) PQ_GO(1, 2, 0)
+    PQ_GO(0, 2, 1) PQ_GO(0, 2, 2) PQ_GO(1, 2, 1) PQ_GO(1, 2, 2)
 #undef PQ_GO
     return cudaErrorInvalidValue;
 }

@@ -212,6 +212,10 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
 {
     constexpr int NCP = NCL * S;
     constexpr int NT = kLapThreads;
+    // slots of a thread's double-double totals: batched permanents keep only the
+    // full product (slots 0..3), the other modes the columns and then the product
+    constexpr int kSlots = MODE == kLapPerm ? 4 : 4 * NCL + 4;
+    constexpr int kFull = MODE == kLapPerm ? 0 : 4 * NCL;
     // chunked suffix / prefix chains of the general (column multiplicity) flavour
     constexpr int CH = NCL >= 4 ? 2 : 1;
     constexpr int CLEN = (NCL + CH - 1) / CH;              // longest chunk
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
         if (threadIdx.x == 0)
             s_step[W] = LapStep{0u, 0u};
 #pragma unroll 4
-        for (int k = 0; k < 4 * NCL + 4; k++)
+        for (int k = 0; k < kSlots; k++)
             tot[k * NT] = 0.0;
     }
     __syncthreads();
@@ -561,8 +565,8 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
             }
         }
         if constexpr (MODE != kLapLoo) {
-            fold(4 * NCL, fullr);
-            fold(4 * NCL + 2, fulli);
+            fold(kFull, fullr);
+            fold(kFull + 2, fulli);
             fullr = fulli = 0.0;
         }
     }
@@ -570,9 +574,9 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
     // ---- CTA reduction (double-double): lanes with equal h hold the same columns.
     // Each warp reduces its totals with shuffles and parks the result in the slots
     // of its lanes 0..S-1; after the barrier NCP + 1 threads add the four warps.
-    auto warp_reduce = [&](int j, double restr, double resti) {
-        dd re{tot[(4 * j) * NT], tot[(4 * j + 1) * NT]};
-        dd im{tot[(4 * j + 2) * NT], tot[(4 * j + 3) * NT]};
+    auto warp_reduce = [&](int slot, double restr, double resti) {
+        dd re{tot[slot * NT], tot[(slot + 1) * NT]};
+        dd im{tot[(slot + 2) * NT], tot[(slot + 3) * NT]};
         dd_add(re, restr); // what has not been folded yet
         dd_add(im, resti);
 #pragma unroll
@@ -580,25 +584,30 @@ __global__ void __launch_bounds__(kLapThreads) laplace_walk_kernel(const LapPara
             dd_add(re, dd_shfl_down(re, delta));
             dd_add(im, dd_shfl_down(im, delta));
         }
-        tot[(4 * j) * NT] = re.hi;
-        tot[(4 * j + 1) * NT] = re.lo;
-        tot[(4 * j + 2) * NT] = im.hi;
-        tot[(4 * j + 3) * NT] = im.lo;
+        tot[slot * NT] = re.hi;
+        tot[(slot + 1) * NT] = re.lo;
+        tot[(slot + 2) * NT] = im.hi;
+        tot[(slot + 3) * NT] = im.lo;
     };
+    if constexpr (MODE != kLapPerm) {
 #pragma unroll
-    for (int j = 0; j < NCL; j++)
-        warp_reduce(j, accr[j], acci[j]);
-    warp_reduce(NCL, fullr, fulli);
+        for (int j = 0; j < NCL; j++)
+            warp_reduce(4 * j, accr[j], acci[j]);
+    }
+    warp_reduce(kFull, fullr, fulli);
     __syncthreads();
     const double *tot0 = reinterpret_cast<const double *>(smA + (size_t)(P.max_D + 1) * NCP);
     for (int k = threadIdx.x; k < NCP + 1; k += NT) {
         // compact column k = j * S + lane; the full product sits in lane 0's slots
-        const int j = k < NCP ? k / S : NCL, lane = k < NCP ? k % S : 0;
+        // (batched permanents: only the product is reduced and stored)
+        if (MODE == kLapPerm && k < NCP)
+            continue;
+        const int slot = k < NCP ? 4 * (k / S) : kFull, lane = k < NCP ? k % S : 0;
         dd re{0.0, 0.0}, im{0.0, 0.0};
         for (int w = 0; w < NT / 32; w++) {
             const double *src = tot0 + w * 32 + lane;
-            dd_add(re, dd{src[(4 * j) * NT], src[(4 * j + 1) * NT]});
-            dd_add(im, dd{src[(4 * j + 2) * NT], src[(4 * j + 3) * NT]});
+            dd_add(re, dd{src[slot * NT], src[(slot + 1) * NT]});
+            dd_add(im, dd{src[(slot + 2) * NT], src[(slot + 3) * NT]});
         }
         double *dst = P.partials + ((size_t)blockIdx.x * (NCP + 1) + k) * 4;
         dst[0] = re.hi;
@@ -617,7 +626,8 @@ static __global__ void __launch_bounds__(128) laplace_reduce_kernel(const LapPar
         return;
     const LapProblem &Q = P.prob[prob];
     const double scale = scalbn(1.0, -Q.exp2);
-    for (int k = threadIdx.x & 31; k < ncp1; k += 32) {
+    // batched permanents: only the full product (index ncp1 - 1) was stored
+    for (int k = (P.perm_only ? ncp1 - 1 : 0) + (threadIdx.x & 31); k < ncp1; k += 32) {
         dd re{0.0, 0.0}, im{0.0, 0.0};
         for (int b = 0; b < Q.nblocks; b++) {
             const double *v = P.partials + ((size_t)(Q.first_block + b) * ncp1 + k) * 4;

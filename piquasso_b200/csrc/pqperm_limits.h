@@ -32,9 +32,11 @@ constexpr int kLapThreads = 128;
 // matrix, then every thread's double-double totals (4 doubles per column of the
 // lane plus 4 for the full product).  Must fit beside ~2.3 KB of static tables.
 constexpr size_t kLapSmemLimit = 224 * 1024;
-inline size_t lap_smem_bytes(int D, int S, int NCL)
+// (perm_only: batched permanents keep only the full product's four slots)
+inline size_t lap_smem_bytes(int D, int S, int NCL, bool perm_only = false)
 {
-    return (size_t)(D + 1) * S * NCL * 16 + (size_t)(4 * NCL + 4) * kLapThreads * 8;
+    return (size_t)(D + 1) * S * NCL * 16 +
+           (size_t)(perm_only ? 4 : 4 * NCL + 4) * kLapThreads * 8;
 }
 
 // Lane split of the Laplace walk for nc active columns: S lanes per Gray
@@ -62,6 +64,16 @@ inline LapVariant laplace_variant(int nc)
         return {4, (nc + 3) / 4};
     // wide problems (few rows, many columns): a whole warp per Gray segment
     return {32, (nc + 31) / 32};
+}
+// Batched permanents (full product only): no per-column accumulators, so one lane
+// holds all the row sums of up to kPermS1MaxCols columns -- no lane exchange, no
+// duplicated step bookkeeping (B200: n = 20 batches 11.0 -> see DESIGN.md).
+constexpr int kPermS1MaxCols = 32;
+inline LapVariant perm_variant(int nc)
+{
+    if (nc <= kPermS1MaxCols)
+        return {1, nc < 1 ? 1 : nc};
+    return laplace_variant(nc);
 }
 
 } // namespace pqperm
