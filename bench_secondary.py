@@ -188,6 +188,37 @@ def run(lib, peak_tflops, rank, world, local_rank, with_reference, sampler_shots
                                   "relerr_gpu_vs_reference": _relerr(complex(v), rv)}
             cfg3[name] = e
         out["cfg3_60modes_24photons"] = cfg3
+        # ---- a detection-probability batch (one interferometer, many
+        # output occupations in one call; the reference loops connector.permanent,
+        # passive/utils.py:131-138) -- 20 single-photon inputs in 60 modes
+        nph, nout = 20, 2000
+        inp20 = np.array([1] * nph + [0] * (60 - nph), dtype=np.int32)
+        outs = np.random.default_rng(7).multinomial(nph, np.ones(60) / 60, size=nout).astype(np.int32)
+        terms = 0.0
+        for r in outs:
+            nz = r[r > 0].astype(np.float64)
+            nz[np.argmin(nz)] -= 1.0
+            terms += float(np.prod(nz + 1.0))
+        flops = terms * (8 * nph + 2)
+        pv, med, mn = _timed(lambda: sampling.detection_probabilities(u60, inp20, outs), 5, warm=1)
+        kms = kernel_ms()
+        e = {"modes": 60, "photons": nph, "outputs": nout, "gray_code_terms": terms,
+             "wall_ms": med * 1e3, "wall_ms_min": mn * 1e3, "kernel_ms": kms,
+             "entry": "piquasso_b200.sampling.detection_probabilities -> pq_perm_batch_c128 (host buffers)",
+             "roofline": {"bound": "fp64", "achieved": flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
+                          "peak": peak_tflops, "unit": "TFLOP/s", "frac": frac(flops, kms)}}
+        if oracle is not None:
+            from scipy.special import factorial
+            nref = 8
+            t0 = time.perf_counter()
+            ref = np.array([oracle.ref_permanent(u60, outs[b], inp20) for b in range(nref)])
+            rt = (time.perf_counter() - t0) / nref
+            pref = np.abs(ref) ** 2 / np.prod(factorial(outs[:nref]), axis=1)
+            e["reference"] = {"kind": "reference", "cores": os.cpu_count(),
+                              "ms_per_output": rt * 1e3, "sample": "%d of the %d outputs" % (nref, nout),
+                              "same_config": True, "speedup_per_output": rt / (med / nout),
+                              "max_relerr_gpu_vs_reference": float(np.max(np.abs(pv[:nref] - pref) / pref))}
+        out["f2_detection_probability_batch"] = e
 
     # ---- configs[3]: the sampler, shots sharded over the ranks ---------------------
     import torch

@@ -506,6 +506,35 @@ def test_permanent_batch_and_detection_probabilities():
         permanent_batch(u, [[1, 0, 0, 0, 0]], [[1, 1, 0, 0, 0]])
 
 
+@pytest.mark.parametrize("photons", [9, 12, 17, 20, 21, 26])
+def test_permanent_batch_one_lane_kernels_against_the_arbiter(photons):
+    """Batched permanents (probability tables, passive/utils.py:131-138 of the
+    reference) walk one lane per Gray segment up to 32 active columns: unit and
+    general column flavours, problems of very different sizes in one call (short
+    segments for the small ones), against the long-double oracle."""
+    from piquasso_b200.sampling import permanent_batch
+    rng = np.random.default_rng(100 + photons)
+    d = 40
+    u = haar(d, 40)
+    # unit columns: `photons` single-photon inputs, outputs with collisions
+    inp = np.zeros(d, dtype=np.int32)
+    inp[rng.choice(d, photons, replace=False)] = 1
+    outs = rng.multinomial(photons, np.ones(d) / d, size=6).astype(np.int32)
+    outs[0] = 0
+    outs[0, :3] = (photons - 2, 1, 1)           # few digits: a handful of terms
+    got = permanent_batch(u, outs, inp)
+    for b in range(len(outs)):
+        want = oracle.permanent(u, outs[b], inp, precision=1)
+        assert close(got[b], want, rtol=1e-10, atol=1e-16), (photons, b)
+    # general flavour: the same photon number through inputs with multiplicities
+    inp2 = rng.multinomial(photons, np.ones(12) / 12).astype(np.int32)
+    inp2 = np.concatenate([inp2, np.zeros(d - 12, dtype=np.int32)])
+    got = permanent_batch(u, outs[:4], inp2)
+    for b in range(4):
+        want = oracle.permanent(u, outs[b], inp2, precision=1)
+        assert close(got[b], want, rtol=1e-10, atol=1e-16), (photons, b, "general")
+
+
 def test_haar_submatrices_up_to_n28_against_the_arbiter():
     """north_star: relative 1e-10 on complex128 Haar-random unitary submatrices.
     The arbiter is the long-double restatement; the reference's own double
