@@ -44,6 +44,7 @@ def _units():
         ("plan", "pqperm_plan.cpp", []),
         ("rng", "pqperm_rng.cpp", []),
         ("generic", "pqperm_kernels_generic.cu", []),
+        ("permhyper", "pqperm_kernels_permhyper.cu", []),
         # every FMA of the double-double arithmetic is explicit: no contraction
         ("arbiter", "pqperm_arbiter.cu", ["-fmad=false"]),
     ]

@@ -60,6 +60,7 @@ struct LapShape {
     int pinned;              // row pinned to delta = +1
     int sum_rows;
     bool unit;
+    bool hyper;              // batched permanents: three binary digits moved to the front
     int src_row[kMaxDigits]; // row feeding digit d
     int mult[kMaxDigits];
     int src_col[kLapMaxCols];
@@ -85,6 +86,7 @@ int lap_shape(int R, int C, const int32_t *rows, const int32_t *cols, LapShape &
         sc += cols[j];
     }
     sh.sum_rows = (int)sr;
+    sh.hyper = false;
     sh.trivial = (R == 0 || C == 0 || sr == 0 || sc == 0); // src/permanent_laplace.cpp:52-57
     if (sh.trivial)
         return PQ_OK;
@@ -134,6 +136,42 @@ int lap_shape(int R, int C, const int32_t *rows, const int32_t *cols, LapShape &
     return PQ_OK;
 }
 
+// Batched permanents, hypercube flavour (pqperm_permhyper.cuh): with unit columns and
+// at least three rows of multiplicity 1, the first three such rows become digits 0..2
+// (the other digits keep their order).  The sum over all Gray tuples does not depend
+// on the order of the digits; only the order of the additions changes.
+bool lap_make_hyper(LapShape &sh)
+{
+    if (!sh.unit || sh.NC < kHyperMinCols || sh.NC > kPermS1MaxCols)
+        return false;
+    int pos[kHyperDigits], found = 0;
+    for (int d = 0; d < sh.D && found < kHyperDigits; d++)
+        if (sh.mult[d] == 1)
+            pos[found++] = d;
+    if (found < kHyperDigits)
+        return false;
+    int mult[kMaxDigits], src[kMaxDigits], n = 0;
+    for (int k = 0; k < kHyperDigits; k++) {
+        mult[n] = 1;
+        src[n++] = sh.src_row[pos[k]];
+    }
+    for (int d = 0; d < sh.D; d++) {
+        bool taken = false;
+        for (int k = 0; k < kHyperDigits; k++)
+            taken = taken || pos[k] == d;
+        if (!taken) {
+            mult[n] = sh.mult[d];
+            src[n++] = sh.src_row[d];
+        }
+    }
+    for (int d = 0; d < sh.D; d++) {
+        sh.mult[d] = mult[d];
+        sh.src_row[d] = src[d];
+    }
+    sh.hyper = true;
+    return true;
+}
+
 // Fills the walk parameters of a described problem: digits 0..q-1 are walked
 // inside a segment of W <= kLapSegLen terms, the rest index the segments.
 // Problems wider than kMaxCols keep their column tables in `wide`.
@@ -151,8 +189,11 @@ void lap_fill(const LapShape &sh, int ncp, LapProblem &q, LapWide *wide = nullpt
     int qd = 0;
     long long W = 1;
     for (int d = 0; d < sh.D; d++) {
-        if (qd == d && qd < kMaxLowDigits && W * (sh.mult[d] + 1) <= seglen &&
-            (min_segs <= 1 || total / (W * (sh.mult[d] + 1)) >= min_segs)) {
+        // (hypercube flavour: the three binary digits of a block are always low)
+        if (qd == d && qd < kMaxLowDigits &&
+            ((sh.hyper && d < kHyperDigits) ||
+             (W * (sh.mult[d] + 1) <= seglen &&
+              (min_segs <= 1 || total / (W * (sh.mult[d] + 1)) >= min_segs)))) {
             W *= (sh.mult[d] + 1);
             qd++;
         }
@@ -186,6 +227,7 @@ const char *const kLapTooWide =
 struct Bucket {
     int S = 0, NCL = 0;
     bool unit = false;
+    bool hyper = false;       // batched permanents: hypercube flavour
     std::vector<LapProblem> probs;
     std::vector<LapWide> wide; // S = 32 only: column tables, aligned with probs
     std::vector<double> a2;   // packed mode
@@ -193,17 +235,19 @@ struct Bucket {
     bool need_full = false;   // some problem has a zero-multiplicity column (it gets the full product)
 };
 
-// buckets[(S index) * 33 * 2 + NCL * 2 + unit]
+// buckets[((S index) * 33 + NCL) * 3 + flavour], flavour 0 general columns, 1 unit
+// columns, 2 unit columns + hypercube
 struct Buckets {
     std::vector<Bucket> b;
-    Buckets() : b(4 * 33 * 2) {}
-    Bucket &get(const LapVariant &v, bool unit)
+    Buckets() : b(4 * 33 * 3) {}
+    Bucket &get(const LapVariant &v, bool unit, bool hyper = false)
     {
         const int si = v.S == 1 ? 0 : (v.S == 2 ? 1 : (v.S == 4 ? 2 : 3));
-        Bucket &k = b[(si * 33 + v.NCL) * 2 + (unit ? 1 : 0)];
+        Bucket &k = b[(si * 33 + v.NCL) * 3 + (hyper ? 2 : (unit ? 1 : 0))];
         k.S = v.S;
         k.NCL = v.NCL;
         k.unit = unit;
+        k.hyper = hyper;
         return k;
     }
     void reset()
@@ -281,6 +325,7 @@ int plan_parallel(int n, F &plan_range, bool &any)
             dst.S = src.S;
             dst.NCL = src.NCL;
             dst.unit = src.unit;
+            dst.hyper = src.hyper;
             dst.max_D = std::max(dst.max_D, src.max_D);
             dst.probs.insert(dst.probs.end(), src.probs.begin(), src.probs.end());
             dst.wide.insert(dst.wide.end(), src.wide.begin(), src.wide.end());
@@ -378,7 +423,9 @@ int run_bucket(DeviceCtx *c, Bucket &bk, const Epilogue *epi)
     // accumulation mode of the walk: full product only (batched permanents), the
     // leave-one-out sums, or both (a caller's zero-multiplicity column gets the full product)
     const int mode = P.perm_only ? 2 : (bk.need_full ? 1 : 0);
-    cudaError_t e = launch_laplace(bk.S, bk.NCL, bk.unit, mode, P, total_blocks, smem, st);
+    cudaError_t e = bk.hyper
+                        ? launch_perm_hyper(bk.NCL, P, total_blocks, smem, st)
+                        : launch_laplace(bk.S, bk.NCL, bk.unit, mode, P, total_blocks, smem, st);
     if (e != cudaSuccess) {
         const std::string what = "launch laplace_walk_kernel<NCL=" + std::to_string(bk.NCL) +
                                  ", S=" + std::to_string(bk.S) + ", unit=" +
@@ -822,6 +869,11 @@ int sampler_step(const double *U, int d, int nshots, const int32_t *out_occ,
 int perm_batch_locked(const double *U, int R, int C, int nprob, const int32_t *row_mult,
                       const int32_t *col_mult, double *out)
 {
+    // PQ_PERM_HYPER=0 keeps every problem on the term-by-term walk (A/B measurements)
+    static const bool use_hyper = [] {
+        const char *e = std::getenv("PQ_PERM_HYPER");
+        return e ? std::atoi(e) != 0 : true;
+    }();
     auto plan_range = [&](int begin, int end, Buckets &buckets, PlanPart &part) {
         LapShape sh;
         for (int b = begin; b < end; b++) {
@@ -845,9 +897,11 @@ int perm_batch_locked(const double *U, int R, int C, int nprob, const int32_t *r
                 out[2 * (size_t)b + 1] = 0.0;
                 continue;
             }
-            // full product only: one lane per segment up to kPermS1MaxCols columns
+            // full product only: one lane per segment up to kPermS1MaxCols columns,
+            // and blocks of 2^3 terms where three binary rows exist
             const LapVariant v = perm_variant(sh.NC);
-            Bucket &bk = buckets.get(v, sh.unit);
+            const bool hyper = use_hyper && lap_make_hyper(sh);
+            Bucket &bk = buckets.get(v, sh.unit, hyper);
             if (lap_smem_bytes(sh.D, v.S, v.NCL, true) > kLapSmemLimit) {
                 part.rc = PQ_ERR_TOO_LARGE;
                 part.err = kLapTooWide;

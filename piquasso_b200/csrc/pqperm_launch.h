@@ -42,6 +42,9 @@ namespace pqperm {
 // mode: 0 leave-one-out sums only, 1 plus the full product, 2 full product only
 cudaError_t launch_laplace(int S, int NCL, bool unitcols, int mode, const LapParams &P,
                            int total_blocks, size_t smem, cudaStream_t stream);
+// batched permanents, hypercube flavour (unit columns, the three lowest digits binary)
+cudaError_t launch_perm_hyper(int nc, const LapParams &P, int total_blocks, size_t smem,
+                              cudaStream_t stream);
 cudaError_t launch_laplace_reduce(const LapParams &P, int ncp1, cudaStream_t stream);
 // out[j] = res[map[j]] for j < ncols (all device pointers)
 cudaError_t launch_laplace_scatter(const double2 *res, const int *map, int ncols, double2 *out,

@@ -27,7 +27,10 @@ constexpr int64_t kMaxSegLenBinary = INT64_C(1) << 14;
 constexpr int64_t kMaxSegLenNary = INT64_C(1) << 10;  // step tables live in shared memory (9 KB)
 
 constexpr int kLapMaxSegLen = 256;     // Laplace: terms per segment (tables in shared memory)
-constexpr int kLapThreads = 128;
+#ifndef PQ_LAP_THREADS
+#define PQ_LAP_THREADS 128
+#endif
+constexpr int kLapThreads = PQ_LAP_THREADS;
 // Dynamic shared memory of one CTA of the Laplace walk: the (D+1) x NCP complex
 // matrix, then every thread's double-double totals (4 doubles per column of the
 // lane plus 4 for the full product).  Must fit beside ~2.3 KB of static tables.
@@ -69,6 +72,10 @@ inline LapVariant laplace_variant(int nc)
 // holds all the row sums of up to kPermS1MaxCols columns -- no lane exchange, no
 // duplicated step bookkeeping (B200: n = 20 batches 11.0 -> see DESIGN.md).
 constexpr int kPermS1MaxCols = 32;
+// ... and, with unit columns and at least kHyperDigits rows of multiplicity 1, the
+// hypercube flavour (pqperm_permhyper.cuh) from kHyperMinCols columns on
+constexpr int kHyperDigits = 3;
+constexpr int kHyperMinCols = 4;
 inline LapVariant perm_variant(int nc)
 {
     if (nc <= kPermS1MaxCols)
