@@ -185,7 +185,18 @@ void lap_fill(const LapShape &sh, int ncp, LapProblem &q, LapWide *wide = nullpt
     long long total = 1;
     for (int d = 0; d < sh.D; d++)
         total *= (sh.mult[d] + 1);
-    const int seglen = total >= kLapBigProblem ? kLapSegLenBig : kLapSegLen;
+    int seglen = total >= kLapBigProblem ? kLapSegLenBig : kLapSegLen;
+    if (sh.hyper && total >= kLapBigProblem) {
+        // the hypercube flavour tabulates BLOCKS of 8 terms: up to 8 x 256 terms per segment
+        // (B200 sweep, n = 24 batches: 256 terms 10.6 ms, 512 10.2, 1024 10.1, 2048 10.2;
+        // n = 20: 8.14 / 8.09 / 8.19 / 8.87)
+        static const int hyper_seglen = [] {
+            const char *e = std::getenv("PQ_HYPER_SEGLEN");
+            const int v = e ? std::atoi(e) : 512;
+            return std::max(64, std::min(v, 8 * kLapMaxSegLen));
+        }();
+        seglen = hyper_seglen;
+    }
     int qd = 0;
     long long W = 1;
     for (int d = 0; d < sh.D; d++) {

@@ -83,3 +83,17 @@ for c5 in ([1, 0, 2, 1, 0, 1], [2, 2, 0, 0, 0, 1], [1, 1, 1, 1, 1, 0]):
     got = permanent_laplace(a5, r5, c5); want = oracle.permanent_laplace(a5, r5, c5)
     assert np.allclose(got, want, rtol=1e-8), ("laplace modes", c5)
 print("round-2 kernels ok, launches:", lib.pq_launch_count())
+
+# batched permanents: one lane per segment (9..32 columns), general columns, and the
+# hypercube flavour (three binary rows low, blocks of 8 terms)
+U20 = unitary_group.rvs(20, random_state=20)
+for ph in (9, 12):
+    inp = np.zeros(20, np.int32); inp[:ph] = 1
+    outs_b = rng.multinomial(ph, np.ones(20) / 20, size=12).astype(np.int32)
+    got = permanent_batch(U20, outs_b, inp)
+    for b in range(0, 12, 3):
+        chk(got[b], oracle.permanent(U20, outs_b[b], inp), ("batch hyper/one-lane", ph, b))
+    inp2 = np.zeros(20, np.int32); inp2[:3] = (ph - 4, 2, 2)
+    got = permanent_batch(U20, outs_b[:4], inp2)
+    chk(got[0], oracle.permanent(U20, outs_b[0], inp2), ("batch general", ph))
+print("batched permanents ok")
