@@ -136,6 +136,25 @@ int lap_shape(int R, int C, const int32_t *rows, const int32_t *cols, LapShape &
     return PQ_OK;
 }
 
+// Batched permanents: a column of multiplicity c is written out as c unit columns while
+// the expanded width fits one lane (what pqperm_plan.cpp does for the single permanent):
+// s_j^c becomes c factors of the product tree instead of a run-time loop.
+void lap_expand_columns(LapShape &sh)
+{
+    if (sh.unit || sh.M > kPermS1MaxCols)
+        return;
+    int src[kPermS1MaxCols], n = 0;
+    for (int j = 0; j < sh.NC; j++)
+        for (int k = 0; k < sh.colmult[j]; k++)
+            src[n++] = sh.src_col[j];
+    for (int j = 0; j < n; j++) {
+        sh.src_col[j] = src[j];
+        sh.colmult[j] = 1;
+    }
+    sh.NC = n;
+    sh.unit = true;
+}
+
 // Batched permanents, hypercube flavour (pqperm_permhyper.cuh): with unit columns and
 // at least three rows of multiplicity 1, the first three such rows become digits 0..2
 // (the other digits keep their order).  The sum over all Gray tuples does not depend
@@ -885,6 +904,8 @@ int perm_batch_locked(const double *U, int R, int C, int nprob, const int32_t *r
         const char *e = std::getenv("PQ_PERM_HYPER");
         return e ? std::atoi(e) != 0 : true;
     }();
+    // segments a problem should yield so that the batch fills ~3 CTAs on each of 148 SMs
+    const int min_segs_fill = (int)std::min<long long>(1 << 20, (3LL * 148 * kLapThreads) / nprob);
     auto plan_range = [&](int begin, int end, Buckets &buckets, PlanPart &part) {
         LapShape sh;
         for (int b = begin; b < end; b++) {
@@ -910,6 +931,7 @@ int perm_batch_locked(const double *U, int R, int C, int nprob, const int32_t *r
             }
             // full product only: one lane per segment up to kPermS1MaxCols columns,
             // and blocks of 2^3 terms where three binary rows exist
+            lap_expand_columns(sh);
             const LapVariant v = perm_variant(sh.NC);
             const bool hyper = use_hyper && lap_make_hyper(sh);
             Bucket &bk = buckets.get(v, sh.unit, hyper);
@@ -920,8 +942,10 @@ int perm_batch_locked(const double *U, int R, int C, int nprob, const int32_t *r
             }
             LapProblem q;
             LapWide w;
-            // small problems: short segments, so that a CTA's threads all get one
-            lap_fill(sh, v.S * v.NCL, q, v.S == 32 ? &w : nullptr, kLapThreads / v.S);
+            // small problems: short segments, so that a CTA's threads all get one; a
+            // batch of a few problems: enough segments to fill the device
+            lap_fill(sh, v.S * v.NCL, q, v.S == 32 ? &w : nullptr,
+                     std::max(kLapThreads / v.S, min_segs_fill));
             q.tag = b;
             q.rowmode[0] = (uint16_t)sh.pinned;
             for (int k = 0; k < sh.D; k++)
