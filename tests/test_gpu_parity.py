@@ -535,6 +535,32 @@ def test_permanent_batch_one_lane_kernels_against_the_arbiter(photons):
         assert close(got[b], want, rtol=1e-10, atol=1e-16), (photons, b, "general")
 
 
+@pytest.mark.parametrize("ncols,extra", [(7, 30), (15, 20), (21, 13)])
+def test_permanent_batch_general_columns_one_lane(ncols, extra):
+    """Batched permanents whose column multiplicities do NOT fit 32 unit columns keep
+    the general flavour (run-time powers s_j^c_j) of the one-lane walk: up to 8, 9..20
+    and 21..32 distinct columns are separate instantiations."""
+    from piquasso_b200.sampling import permanent_batch
+    rng = np.random.default_rng(7 * ncols)
+    d = 30
+    u = haar(d, 30)
+    inp = np.zeros(d, dtype=np.int32)
+    inp[:ncols] = 1
+    inp[:extra] += 1 if extra <= ncols else 0
+    if extra > ncols:                      # pile the surplus onto the first columns
+        inp[: extra % ncols] += extra // ncols + 1
+        inp[extra % ncols: ncols] += extra // ncols
+    photons = int(inp.sum())
+    assert photons > 32 and np.count_nonzero(inp) == ncols
+    outs = np.zeros((3, d), dtype=np.int32)
+    for b in range(3):
+        outs[b, rng.choice(d, 6, replace=False)] = rng.multinomial(photons, np.ones(6) / 6)
+    got = permanent_batch(u, outs, inp)
+    for b in range(3):
+        want = oracle.permanent(u, outs[b], inp, precision=1)
+        assert close(got[b], want, rtol=1e-9, atol=1e-300), (ncols, b, got[b], want)
+
+
 def test_haar_submatrices_up_to_n28_against_the_arbiter():
     """north_star: relative 1e-10 on complex128 Haar-random unitary submatrices.
     The arbiter is the long-double restatement; the reference's own double
