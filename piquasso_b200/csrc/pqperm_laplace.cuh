@@ -173,7 +173,8 @@ __device__ __forceinline__ void others_product(double lr, double li, double &olr
 }
 
 // Slots of a thread's double-double totals in shared memory: column j uses
-// slots 4j .. 4j+3 (re hi, re lo, im hi, im lo), the full product 4 NCL .. 4 NCL+3.
+// slots 4j .. 4j+3 (re hi, re lo, im hi, im lo), the full product 4 NCL .. 4 NCL+3
+// (batched permanents, mode kLapPerm: only the product, in slots 0 .. 3).
 __device__ __forceinline__ void dd_fold(double *tot, int slot, int nt, double v)
 {
     // tot[slot] (hi), tot[slot + 1] (lo) += v   (TwoSum)
