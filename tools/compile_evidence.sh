@@ -24,8 +24,14 @@ for part in "2 31 40"; do
     echo "## pqperm_kernels_binary.cu part $1 (NC $2..$3)" >> $OUT
     nvcc $FLAGS -DPQ_BIN_PART=$1 -DPQ_BIN_LO=$2 -DPQ_BIN_HI=$3 -c $CS/pqperm_kernels_binary.cu -o /tmp/ev_bin$1.o 2>&1 | summarise >> $OUT
 done
-echo "## pqperm_kernels_laplace.cu (unit columns)" >> $OUT
-nvcc $FLAGS -DPQ_LAP_UNIT=1 -c $CS/pqperm_kernels_laplace.cu -o /tmp/ev_lap.o 2>&1 | summarise >> $OUT
+echo "## pqperm_kernels_laplace.cu (unit columns, leave-one-out sums: the sampler's kernels)" >> $OUT
+nvcc $FLAGS -DPQ_LAP_UNIT=1 -DPQ_LAP_MODE=0 -c $CS/pqperm_kernels_laplace.cu -o /tmp/ev_lap.o 2>&1 | summarise >> $OUT
+for part in 0 1 2; do
+    echo "## pqperm_kernels_laplace.cu (unit columns, full product only: batched permanents, part $part)" >> $OUT
+    nvcc $FLAGS -DPQ_LAP_UNIT=1 -DPQ_LAP_MODE=2 -DPQ_LAP_PART=$part -c $CS/pqperm_kernels_laplace.cu -o /tmp/ev_lapp.o 2>&1 | summarise >> $OUT
+done
+echo "## pqperm_kernels_permhyper.cu (batched permanents, hypercube flavour)" >> $OUT
+nvcc $FLAGS -c $CS/pqperm_kernels_permhyper.cu -o /tmp/ev_hyp.o 2>&1 | summarise >> $OUT
 echo "## pqperm_kernels_generic.cu" >> $OUT
 nvcc $FLAGS -c $CS/pqperm_kernels_generic.cu -o /tmp/ev_gen.o 2>&1 | summarise >> $OUT
 echo "## pqperm_arbiter.cu" >> $OUT
