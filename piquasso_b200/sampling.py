@@ -96,8 +96,9 @@ def permanent_batch(matrix, rows_batch, cols_batch):
     if a.ndim != 2:
         raise ValueError("matrix must be 2-dimensional")
     R, C = a.shape
-    rb = np.ascontiguousarray(np.asarray(rows_batch).astype(np.int32, casting="unsafe")).reshape(-1, R)
-    cb = np.asarray(cols_batch).astype(np.int32, casting="unsafe")
+    # (no copy when the caller already holds contiguous int32 arrays)
+    rb = np.ascontiguousarray(np.asarray(rows_batch), dtype=np.int32).reshape(-1, R)
+    cb = np.asarray(np.asarray(cols_batch), dtype=np.int32)
     if cb.ndim == 1:
         cb = np.broadcast_to(cb, (rb.shape[0], C))
     cb = np.ascontiguousarray(cb).reshape(-1, C)
