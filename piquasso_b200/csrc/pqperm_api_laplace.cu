@@ -906,95 +906,104 @@ int perm_batch_locked(const double *U, int R, int C, int nprob, const int32_t *r
     }();
     // segments a problem should yield so that the batch fills ~3 CTAs on each of 148 SMs
     const int min_segs_fill = (int)std::min<long long>(1 << 20, (3LL * 148 * kLapThreads) / nprob);
-    auto plan_range = [&](int begin, int end, Buckets &buckets, PlanPart &part) {
-        LapShape sh;
-        for (int b = begin; b < end; b++) {
-            const int32_t *rw = row_mult + (size_t)b * R, *cl = col_mult + (size_t)b * C;
-            part.rc = lap_shape(R, C, rw, cl, sh, part.err);
-            if (part.rc)
-                return;
-            long long sr = 0, sc = 0;
-            for (int i = 0; i < R; i++)
-                sr += rw[i];
-            for (int j = 0; j < C; j++)
-                sc += cl[j];
-            if (sr != sc) { // src/permanent.cpp:97-104
-                part.rc = PQ_ERR_SUM_MISMATCH;
-                part.err = "Number of input and output states should be equal (problem " +
-                           std::to_string(b) + ")";
-                return;
-            }
-            if (sh.trivial) { // src/permanent.cpp:106-108
-                out[2 * (size_t)b] = 1.0;
-                out[2 * (size_t)b + 1] = 0.0;
-                continue;
-            }
-            // full product only: one lane per segment up to kPermS1MaxCols columns,
-            // and blocks of 2^3 terms where three binary rows exist
-            lap_expand_columns(sh);
-            const LapVariant v = perm_variant(sh.NC);
-            const bool hyper = use_hyper && lap_make_hyper(sh);
-            Bucket &bk = buckets.get(v, sh.unit, hyper);
-            if (lap_smem_bytes(sh.D, v.S, v.NCL, true) > kLapSmemLimit) {
-                part.rc = PQ_ERR_TOO_LARGE;
-                part.err = kLapTooWide;
-                return;
-            }
-            LapProblem q;
-            LapWide w;
-            // small problems: short segments, so that a CTA's threads all get one; a
-            // batch of a few problems: enough segments to fill the device
-            lap_fill(sh, v.S * v.NCL, q, v.S == 32 ? &w : nullptr,
-                     std::max(kLapThreads / v.S, min_segs_fill));
-            q.tag = b;
-            q.rowmode[0] = (uint16_t)sh.pinned;
-            for (int k = 0; k < sh.D; k++)
-                q.rowmode[k + 1] = (uint16_t)sh.src_row[k];
-            bk.max_D = std::max(bk.max_D, sh.D);
-            bk.probs.push_back(q);
-            if (v.S == 32)
-                bk.wide.push_back(w);
-            part.any = true;
-        }
-    };
-    bool any = false;
-    {
-        const int prc = plan_parallel(nprob, plan_range, any);
-        if (prc)
-            return prc;
-    }
-    if (!any)
-        return PQ_OK;
+    // Large batches go through in chunks: 440 bytes of descriptor per problem, staged in
+    // pinned host memory and uploaded, stay bounded (58 MB) however many problems come.
+    constexpr int kChunk = 1 << 17;
     DeviceCtx *c = nullptr;
-    int rc = ctx_get(g_devices[0], &c);
-    if (rc)
-        return rc;
-    std::lock_guard<std::mutex> dev_lock(c->mu);
-    // gather mode needs a square leading dimension only for addressing: ldu = C
-    const size_t ubytes = (size_t)R * C * sizeof(double2);
-    if ((rc = grow_dev(c, 4, ubytes)))
-        return rc;
-    c->u_host.clear(); // the sampler's resident interferometer is overwritten
-    PQ_CUDA(cudaMemcpyAsync(c->d_lap[4], U, ubytes, cudaMemcpyHostToDevice, c->stream));
+    std::unique_lock<std::mutex> dev_lock;
     Epilogue epi;
-    epi.d_U = reinterpret_cast<const double2 *>(c->d_lap[4]);
-    epi.ldu = C;
-    epi.perm_only = true;
-    c->last_kernel_ms = -1.0;
-    for (Bucket &bk : g_buckets.b) {
-        if (bk.probs.empty())
-            continue;
-        rc = run_bucket(c, bk, &epi);
-        if (rc)
-            return rc;
-        const int ncp1 = bk.S * bk.NCL + 1;
-        const double *ho = reinterpret_cast<const double *>(c->h_lap[2]);
-        for (size_t i = 0; i < bk.probs.size(); i++) {
-            const int b = bk.probs[i].tag;
-            out[2 * (size_t)b] = ho[(i * ncp1 + (ncp1 - 1)) * 2];
-            out[2 * (size_t)b + 1] = ho[(i * ncp1 + (ncp1 - 1)) * 2 + 1];
+    int rc = PQ_OK;
+    for (int base = 0; base < nprob; base += kChunk) {
+        const int nchunk = std::min(kChunk, nprob - base);
+        auto plan_range = [&](int begin, int end, Buckets &buckets, PlanPart &part) {
+            LapShape sh;
+            for (int b = base + begin; b < base + end; b++) {
+                const int32_t *rw = row_mult + (size_t)b * R, *cl = col_mult + (size_t)b * C;
+                part.rc = lap_shape(R, C, rw, cl, sh, part.err);
+                if (part.rc)
+                    return;
+                long long sr = 0, sc = 0;
+                for (int i = 0; i < R; i++)
+                    sr += rw[i];
+                for (int j = 0; j < C; j++)
+                    sc += cl[j];
+                if (sr != sc) { // src/permanent.cpp:97-104
+                    part.rc = PQ_ERR_SUM_MISMATCH;
+                    part.err = "Number of input and output states should be equal (problem " +
+                               std::to_string(b) + ")";
+                    return;
+                }
+                if (sh.trivial) { // src/permanent.cpp:106-108
+                    out[2 * (size_t)b] = 1.0;
+                    out[2 * (size_t)b + 1] = 0.0;
+                    continue;
+                }
+                // full product only: one lane per segment up to kPermS1MaxCols columns,
+                // and blocks of 2^3 terms where three binary rows exist
+                lap_expand_columns(sh);
+                const LapVariant v = perm_variant(sh.NC);
+                const bool hyper = use_hyper && lap_make_hyper(sh);
+                Bucket &bk = buckets.get(v, sh.unit, hyper);
+                if (lap_smem_bytes(sh.D, v.S, v.NCL, true) > kLapSmemLimit) {
+                    part.rc = PQ_ERR_TOO_LARGE;
+                    part.err = kLapTooWide;
+                    return;
+                }
+                LapProblem q;
+                LapWide w;
+                // small problems: short segments, so that a CTA's threads all get one; a
+                // batch of a few problems: enough segments to fill the device
+                lap_fill(sh, v.S * v.NCL, q, v.S == 32 ? &w : nullptr,
+                         std::max(kLapThreads / v.S, min_segs_fill));
+                q.tag = b;
+                q.rowmode[0] = (uint16_t)sh.pinned;
+                for (int k = 0; k < sh.D; k++)
+                    q.rowmode[k + 1] = (uint16_t)sh.src_row[k];
+                bk.max_D = std::max(bk.max_D, sh.D);
+                bk.probs.push_back(q);
+                if (v.S == 32)
+                    bk.wide.push_back(w);
+                part.any = true;
+            }
+        };
+        bool any = false;
+        {
+            const int prc = plan_parallel(nchunk, plan_range, any);
+            if (prc)
+                return prc;
         }
-    }
+        if (!any)
+            continue;
+        if (!c) {
+            if ((rc = ctx_get(g_devices[0], &c)))
+                return rc;
+            dev_lock = std::unique_lock<std::mutex>(c->mu);
+            // gather mode needs a square leading dimension only for addressing: ldu = C
+            const size_t ubytes = (size_t)R * C * sizeof(double2);
+            if ((rc = grow_dev(c, 4, ubytes)))
+                return rc;
+            c->u_host.clear(); // the sampler's resident interferometer is overwritten
+            PQ_CUDA(cudaMemcpyAsync(c->d_lap[4], U, ubytes, cudaMemcpyHostToDevice, c->stream));
+            epi.d_U = reinterpret_cast<const double2 *>(c->d_lap[4]);
+            epi.ldu = C;
+            epi.perm_only = true;
+            c->last_kernel_ms = -1.0;
+        }
+        for (Bucket &bk : g_buckets.b) {
+            if (bk.probs.empty())
+                continue;
+            rc = run_bucket(c, bk, &epi);
+            if (rc)
+                return rc;
+            const int ncp1 = bk.S * bk.NCL + 1;
+            const double *ho = reinterpret_cast<const double *>(c->h_lap[2]);
+            for (size_t i = 0; i < bk.probs.size(); i++) {
+                const int b = bk.probs[i].tag;
+                out[2 * (size_t)b] = ho[(i * ncp1 + (ncp1 - 1)) * 2];
+                out[2 * (size_t)b + 1] = ho[(i * ncp1 + (ncp1 - 1)) * 2 + 1];
+            }
+        }
+    } // chunks
     return PQ_OK;
 }
 

@@ -46,3 +46,16 @@ for case in range(cases):
         worst = max(worst, err)
         nprob += 1
 print("fuzz_batch: %d cases, %d problems compared, worst relative difference %.2e" % (cases, nprob, worst))
+
+# one batch larger than the chunk the library plans and uploads at a time (2^17 problems)
+m, ph, B = 16, 5, 300000
+U = unitary_group.rvs(m, random_state=16)
+inp = np.zeros(m, np.int32); inp[:ph] = 1
+outs = rng.multinomial(ph, np.ones(m) / m, size=B).astype(np.int32)
+got = permanent_batch(U, outs, inp)
+w = 0.0
+for b in list(rng.choice(B, 40, replace=False)) + [0, 131071, 131072, 262143, 262144, B - 1]:
+    want = complex(permanent(U, outs[b], inp))
+    w = max(w, abs(got[b] - want) / max(abs(want), 1e-300))
+assert w < 1e-9, w
+print("chunked batch of %d problems: worst relative difference %.2e" % (B, w))
