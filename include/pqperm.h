@@ -133,7 +133,8 @@ int pq_perm_laplace_batch_c128(int nprob, const double *A, const int64_t *a_off,
  * rows=output) (piquasso/_simulators/passive/utils.py:131-138,
  * probabilities.py:26-54) for tables of detection amplitudes: the matrix is
  * uploaded once and every CTA gathers its own minor.  A sum mismatch in any
- * problem fails the whole call with PQ_ERR_SUM_MISMATCH.
+ * problem fails the whole call with PQ_ERR_SUM_MISMATCH.  Any number of problems:
+ * the batch is planned (on host threads), staged and launched in chunks of 2^17.
  * ------------------------------------------------------------------- */
 int pq_perm_batch_c128(const double *A, int R, int C, int nprob, const int32_t *row_mult,
                        const int32_t *col_mult, double *out);
