@@ -112,113 +112,118 @@ def run(lib, peak_tflops, rank, world, local_rank, with_reference, sampler_shots
         return flops / (ms * 1e-3) / 1e12 / peak_tflops
 
     if rank == 0:
-        _lib.check(lib.pq_set_devices((ctypes.c_int32 * 1)(dev), 1))
-        # ---- configs[0]: n = 20 through the pybind11 module -----------------------
-        native = os.path.join(ROOT, "piquasso_b200", "native")
-        if native not in sys.path:
-            sys.path.insert(0, native)
+        # a failure in one of these single-rank sections must not take the headline line (or the
+        # collective sampler section below) with it: it is reported in the record instead
         try:
-            import permanent as pyb
-            entry = pyb.permanent
-            binding = "pybind11 module piquasso_b200/native/permanent (drop-in for piquasso._math.permanent)"
-        except ImportError:
-            entry = perm_ctypes
-            binding = "ctypes mirror piquasso_b200._math.permanent (pybind11 module not built)"
-        for name, n, reps, ref_reps in (("cfg1_n20", 20, 300, 5), ("n24", 24, 50, 3),
-                                        ("cfg2_n30", 30, 5, 1)):
-            u = _haar(n, n)
-            ones = np.ones(n, dtype=np.int32)
-            v, med, mn = _timed(lambda: entry(u, ones, ones), reps)
+            _lib.check(lib.pq_set_devices((ctypes.c_int32 * 1)(dev), 1))
+            # ---- configs[0]: n = 20 through the pybind11 module -----------------------
+            native = os.path.join(ROOT, "piquasso_b200", "native")
+            if native not in sys.path:
+                sys.path.insert(0, native)
+            try:
+                import permanent as pyb
+                entry = pyb.permanent
+                binding = "pybind11 module piquasso_b200/native/permanent (drop-in for piquasso._math.permanent)"
+            except ImportError:
+                entry = perm_ctypes
+                binding = "ctypes mirror piquasso_b200._math.permanent (pybind11 module not built)"
+            for name, n, reps, ref_reps in (("cfg1_n20", 20, 300, 5), ("n24", 24, 50, 3),
+                                            ("cfg2_n30", 30, 5, 1)):
+                u = _haar(n, n)
+                ones = np.ones(n, dtype=np.int32)
+                v, med, mn = _timed(lambda: entry(u, ones, ones), reps)
+                kms = kernel_ms()
+                # the same call with the library's per-launch CUDA-event pair switched off
+                # (pq_set_timing(0): what a latency-sensitive caller would configure)
+                lib.pq_set_timing(0)
+                _, med_off, _ = _timed(lambda: entry(u, ones, ones), reps)
+                lib.pq_set_timing(1)
+                terms = 2 ** (n - 1)
+                flops = terms * (8 * n + 2)
+                p = pqplan.plan(ones, ones)
+                e = {"n": n, "terms": terms, "wall_ms": med * 1e3, "wall_ms_min": mn * 1e3,
+                     "wall_ms_timing_off": med_off * 1e3,
+                     "kernel_ms": kms, "terms_per_s": terms / med, "binding": binding,
+                     "plan": {"kernel": p["kernel"], "seg_len": p["seg_len"]},
+                     "roofline": {"bound": "fp64", "achieved": flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
+                                  "peak": peak_tflops, "unit": "TFLOP/s", "frac": frac(flops, kms)},
+                     "value": [complex(v).real, complex(v).imag]}
+                if oracle is not None:
+                    rv, rmed, _ = _timed(lambda: oracle.ref_permanent(u, ones, ones), ref_reps,
+                                         warm=1 if n <= 24 else 0)
+                    e["reference"] = {"kind": "reference", "cores": os.cpu_count(), "wall_ms": rmed * 1e3,
+                                      "same_config": True, "speedup_wall": rmed / med,
+                                      "relerr_gpu_vs_reference": _relerr(complex(v), rv)}
+                if n == 30:
+                    try:
+                        gold = json.load(open(os.path.join(ROOT, "tests", "golden", "arbiter.json")))
+                        g = [x for x in gold["haar"] if x["n"] == 30 and x["precision"] == 1][0]
+                        hi, lo = complex(*g["hi"]), complex(*g["lo"])
+                        e["relerr_gpu_vs_long_double_arbiter"] = abs((complex(v) - hi) - lo) / abs(hi)
+                        if "reference_cpp" in g:
+                            e["relerr_reference_vs_long_double_arbiter"] = abs(
+                                (complex(*g["reference_cpp"]) - hi) - lo) / abs(hi)
+                    except (OSError, IndexError, KeyError):
+                        pass
+                out[name] = e
+            # ---- configs[2]: 60 modes / 24 photons, unfiltered d x d call -------------
+            u60 = _haar(60, 60)
+            cfg3 = {}
+            for name, (rows, cols) in cfg3_cases().items():
+                rows, cols = rows.astype(np.int32), cols.astype(np.int32)
+                p = pqplan.plan(rows, cols)
+                v, med, mn = _timed(lambda: entry(u60, rows, cols), 50)
+                kms = kernel_ms()
+                lib.pq_set_timing(0)
+                _, med_off, _ = _timed(lambda: entry(u60, rows, cols), 50)
+                lib.pq_set_timing(1)
+                flops = p["idx_max"] * p["flops_per_term"]
+                e = {"idx_max": p["idx_max"], "flops_per_term": p["flops_per_term"],
+                     "wall_ms": med * 1e3, "wall_ms_min": mn * 1e3,
+                     "wall_ms_timing_off": med_off * 1e3, "kernel_ms": kms,
+                     "plan": {"kernel": p["kernel"], "seg_len": p["seg_len"]},
+                     "roofline": {"bound": "fp64", "achieved": flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
+                                  "peak": peak_tflops, "unit": "TFLOP/s", "frac": frac(flops, kms)}}
+                if oracle is not None and p["idx_max"] <= 2 ** 30:
+                    rv, rmed, _ = _timed(lambda: oracle.ref_permanent(u60, rows, cols), 3, warm=1)
+                    e["reference"] = {"kind": "reference", "cores": os.cpu_count(), "wall_ms": rmed * 1e3,
+                                      "same_config": True, "speedup_wall": rmed / med,
+                                      "relerr_gpu_vs_reference": _relerr(complex(v), rv)}
+                cfg3[name] = e
+            out["cfg3_60modes_24photons"] = cfg3
+            # ---- a detection-probability batch (one interferometer, many
+            # output occupations in one call; the reference loops connector.permanent,
+            # passive/utils.py:131-138) -- 20 single-photon inputs in 60 modes
+            nph, nout = 20, 2000
+            inp20 = np.array([1] * nph + [0] * (60 - nph), dtype=np.int32)
+            outs = np.random.default_rng(7).multinomial(nph, np.ones(60) / 60, size=nout).astype(np.int32)
+            terms = 0.0
+            for r in outs:
+                nz = r[r > 0].astype(np.float64)
+                nz[np.argmin(nz)] -= 1.0
+                terms += float(np.prod(nz + 1.0))
+            flops = terms * (8 * nph + 2)
+            pv, med, mn = _timed(lambda: sampling.detection_probabilities(u60, inp20, outs), 5, warm=1)
             kms = kernel_ms()
-            # the same call with the library's per-launch CUDA-event pair switched off
-            # (pq_set_timing(0): what a latency-sensitive caller would configure)
-            lib.pq_set_timing(0)
-            _, med_off, _ = _timed(lambda: entry(u, ones, ones), reps)
-            lib.pq_set_timing(1)
-            terms = 2 ** (n - 1)
-            flops = terms * (8 * n + 2)
-            p = pqplan.plan(ones, ones)
-            e = {"n": n, "terms": terms, "wall_ms": med * 1e3, "wall_ms_min": mn * 1e3,
-                 "wall_ms_timing_off": med_off * 1e3,
-                 "kernel_ms": kms, "terms_per_s": terms / med, "binding": binding,
-                 "plan": {"kernel": p["kernel"], "seg_len": p["seg_len"]},
-                 "roofline": {"bound": "fp64", "achieved": flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
-                              "peak": peak_tflops, "unit": "TFLOP/s", "frac": frac(flops, kms)},
-                 "value": [complex(v).real, complex(v).imag]}
-            if oracle is not None:
-                rv, rmed, _ = _timed(lambda: oracle.ref_permanent(u, ones, ones), ref_reps,
-                                     warm=1 if n <= 24 else 0)
-                e["reference"] = {"kind": "reference", "cores": os.cpu_count(), "wall_ms": rmed * 1e3,
-                                  "same_config": True, "speedup_wall": rmed / med,
-                                  "relerr_gpu_vs_reference": _relerr(complex(v), rv)}
-            if n == 30:
-                try:
-                    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "arbiter.json")))
-                    g = [x for x in gold["haar"] if x["n"] == 30 and x["precision"] == 1][0]
-                    hi, lo = complex(*g["hi"]), complex(*g["lo"])
-                    e["relerr_gpu_vs_long_double_arbiter"] = abs((complex(v) - hi) - lo) / abs(hi)
-                    if "reference_cpp" in g:
-                        e["relerr_reference_vs_long_double_arbiter"] = abs(
-                            (complex(*g["reference_cpp"]) - hi) - lo) / abs(hi)
-                except (OSError, IndexError, KeyError):
-                    pass
-            out[name] = e
-        # ---- configs[2]: 60 modes / 24 photons, unfiltered d x d call -------------
-        u60 = _haar(60, 60)
-        cfg3 = {}
-        for name, (rows, cols) in cfg3_cases().items():
-            rows, cols = rows.astype(np.int32), cols.astype(np.int32)
-            p = pqplan.plan(rows, cols)
-            v, med, mn = _timed(lambda: entry(u60, rows, cols), 50)
-            kms = kernel_ms()
-            lib.pq_set_timing(0)
-            _, med_off, _ = _timed(lambda: entry(u60, rows, cols), 50)
-            lib.pq_set_timing(1)
-            flops = p["idx_max"] * p["flops_per_term"]
-            e = {"idx_max": p["idx_max"], "flops_per_term": p["flops_per_term"],
-                 "wall_ms": med * 1e3, "wall_ms_min": mn * 1e3,
-                 "wall_ms_timing_off": med_off * 1e3, "kernel_ms": kms,
-                 "plan": {"kernel": p["kernel"], "seg_len": p["seg_len"]},
+            e = {"modes": 60, "photons": nph, "outputs": nout, "gray_code_terms": terms,
+                 "wall_ms": med * 1e3, "wall_ms_min": mn * 1e3, "kernel_ms": kms,
+                 "entry": "piquasso_b200.sampling.detection_probabilities -> pq_perm_batch_c128 (host buffers)",
                  "roofline": {"bound": "fp64", "achieved": flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
                               "peak": peak_tflops, "unit": "TFLOP/s", "frac": frac(flops, kms)}}
-            if oracle is not None and p["idx_max"] <= 2 ** 30:
-                rv, rmed, _ = _timed(lambda: oracle.ref_permanent(u60, rows, cols), 3, warm=1)
-                e["reference"] = {"kind": "reference", "cores": os.cpu_count(), "wall_ms": rmed * 1e3,
-                                  "same_config": True, "speedup_wall": rmed / med,
-                                  "relerr_gpu_vs_reference": _relerr(complex(v), rv)}
-            cfg3[name] = e
-        out["cfg3_60modes_24photons"] = cfg3
-        # ---- a detection-probability batch (one interferometer, many
-        # output occupations in one call; the reference loops connector.permanent,
-        # passive/utils.py:131-138) -- 20 single-photon inputs in 60 modes
-        nph, nout = 20, 2000
-        inp20 = np.array([1] * nph + [0] * (60 - nph), dtype=np.int32)
-        outs = np.random.default_rng(7).multinomial(nph, np.ones(60) / 60, size=nout).astype(np.int32)
-        terms = 0.0
-        for r in outs:
-            nz = r[r > 0].astype(np.float64)
-            nz[np.argmin(nz)] -= 1.0
-            terms += float(np.prod(nz + 1.0))
-        flops = terms * (8 * nph + 2)
-        pv, med, mn = _timed(lambda: sampling.detection_probabilities(u60, inp20, outs), 5, warm=1)
-        kms = kernel_ms()
-        e = {"modes": 60, "photons": nph, "outputs": nout, "gray_code_terms": terms,
-             "wall_ms": med * 1e3, "wall_ms_min": mn * 1e3, "kernel_ms": kms,
-             "entry": "piquasso_b200.sampling.detection_probabilities -> pq_perm_batch_c128 (host buffers)",
-             "roofline": {"bound": "fp64", "achieved": flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
-                          "peak": peak_tflops, "unit": "TFLOP/s", "frac": frac(flops, kms)}}
-        if oracle is not None:
-            from scipy.special import factorial
-            nref = 8
-            t0 = time.perf_counter()
-            ref = np.array([oracle.ref_permanent(u60, outs[b], inp20) for b in range(nref)])
-            rt = (time.perf_counter() - t0) / nref
-            pref = np.abs(ref) ** 2 / np.prod(factorial(outs[:nref]), axis=1)
-            e["reference"] = {"kind": "reference", "cores": os.cpu_count(),
-                              "ms_per_output": rt * 1e3, "sample": "%d of the %d outputs" % (nref, nout),
-                              "same_config": True, "speedup_per_output": rt / (med / nout),
-                              "max_relerr_gpu_vs_reference": float(np.max(np.abs(pv[:nref] - pref) / pref))}
-        out["f2_detection_probability_batch"] = e
+            if oracle is not None:
+                from scipy.special import factorial
+                nref = 8
+                t0 = time.perf_counter()
+                ref = np.array([oracle.ref_permanent(u60, outs[b], inp20) for b in range(nref)])
+                rt = (time.perf_counter() - t0) / nref
+                pref = np.abs(ref) ** 2 / np.prod(factorial(outs[:nref]), axis=1)
+                e["reference"] = {"kind": "reference", "cores": os.cpu_count(),
+                                  "ms_per_output": rt * 1e3, "sample": "%d of the %d outputs" % (nref, nout),
+                                  "same_config": True, "speedup_per_output": rt / (med / nout),
+                                  "max_relerr_gpu_vs_reference": float(np.max(np.abs(pv[:nref] - pref) / pref))}
+            out["f2_detection_probability_batch"] = e
+        except Exception as exc:  # noqa: BLE001
+            out["error"] = "%s: %s" % (type(exc).__name__, exc)
 
     # ---- configs[3]: the sampler, shots sharded over the ranks ---------------------
     import torch
