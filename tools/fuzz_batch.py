@@ -11,6 +11,7 @@ from piquasso_b200.sampling import permanent_batch
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 120
 rng = np.random.default_rng(2026)
 worst = 0.0
+worst_case = None
 nprob = 0
 for case in range(cases):
     m = int(rng.integers(3, 41))
@@ -43,9 +44,17 @@ for case in range(cases):
         if err > 1e-7:
             print("MISMATCH case", case, "m", m, "photons", ph, "b", b, got[b], want, err,
                   "rows", outs[b][outs[b] > 0], "cols", inp[inp > 0], flush=True)
-        worst = max(worst, err)
+        if err > worst:
+            worst, worst_case = err, (U, outs[b].copy(), inp.copy(), got[b], want)
         nprob += 1
 print("fuzz_batch: %d cases, %d problems compared, worst relative difference %.2e" % (cases, nprob, worst))
+if worst_case is not None:
+    # who is off in the worst case?  both against the long-double oracle
+    import oracle
+    U_, r_, c_, gb, gs = worst_case
+    ref = oracle.permanent(U_, r_, c_, precision=1)
+    print("  worst case rows %s cols %s: batch %.2e, single %.2e from the long-double oracle"
+          % (r_[r_ > 0], c_[c_ > 0], abs(gb - ref) / abs(ref), abs(gs - ref) / abs(ref)))
 
 # one batch larger than the chunk the library plans and uploads at a time (2^17 problems)
 m, ph, B = 16, 5, 300000
