@@ -348,9 +348,10 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
     ``overlap`` > 1 runs shot batches in that many worker threads (host
     bookkeeping and planning of one batch under the GPU time of another; the
     library serialises the device phases).  The default is two equal halves from
-    1000 shots on (config 4 on B200: 10^4 shots 1.52 -> 1.47 s, 5000 shots 0.735 -> 0.69 s,
-    1250 shots -- a rank's share at 8 GPUs -- 0.20 -> 0.187 s; the GPU time sits in the last
-    three photons, so the gain is a few percent) and a single batch below;
+    2000 shots on (config 4 on B200: 10^4 shots 1.52 -> 1.47 s, 5000 shots 0.735 -> 0.69 s,
+    2500 shots 0.37 -> 0.35 s; the GPU time sits in the last three photons, so the gain is
+    a few percent) and a single batch below (1250 shots gain 6 % on an idle host, but that
+    is a rank's share at 8 GPUs, where eight processes already share the host's cores);
     ``batch_shots`` fixes the batch size instead.  ``devices`` (CUDA device indices) shards the shots over several
     GPUs inside this process, one host thread per device.  The result does not
     depend on any of them.  ``as_array`` returns the samples as one (shots, d) int32
@@ -474,9 +475,9 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
 
 
 # shots below which one batch is not worth splitting for host/GPU overlap
-_OVERLAP_MIN_SHOTS = 1000
+_OVERLAP_MIN_SHOTS = 2000
 # shots from which two overlapping halves are the default
-_OVERLAP_DEFAULT_SHOTS = 1000
+_OVERLAP_DEFAULT_SHOTS = 2000
 # batch sizes (fractions of the shots) handed to more than two worker threads, in this order
 _OVERLAP_FRACTIONS = (0.375, 0.25, 0.25, 0.125)
 
