@@ -254,7 +254,8 @@ typedef struct pq_plan_info {
     int32_t active_rows;   /* Gray digits with radix >= 2 */
     int32_t active_cols;   /* columns with multiplicity > 0 */
     int32_t low_digits;    /* digits walked inside a segment */
-    int32_t kernel;        /* 1 = generic n-ary walk, 2 = binary constant-bank walk */
+    int32_t kernel;        /* 1 = generic n-ary walk, 2 = binary constant-bank walk
+                              (pq_perm_batch_plan: 3 / 4, see there) */
     int32_t cols_padded;   /* register-resident row sums per thread */
     int32_t sum_rows;
     int32_t trivial;       /* 1 = handled by a reference early-out */
@@ -281,6 +282,15 @@ int pq_perm_job_destroy(pq_perm_job *job);
 /* Plan that pq_perm_c128 would use for these multiplicities (no GPU needed). */
 int pq_perm_plan(int R, int C, const int32_t *rows, const int32_t *cols,
                  pq_plan_info *info);
+
+/* Plan that pq_perm_batch_c128 would use for ONE problem of a batch of `nprob`
+ * (no GPU needed).  kernel: 3 = batched walk, term by term (one lane per Gray
+ * segment up to 32 columns, lane-split beyond), 4 = batched walk, hypercube
+ * flavour (three rows of multiplicity 1 are the low digits, blocks of 8 terms).
+ * cols_padded = columns the kernel holds after column multiplicities were written
+ * out as unit columns (when they fit); seg_len * nseg = idx_max always. */
+int pq_perm_batch_plan(int R, int C, const int32_t *rows, const int32_t *cols, int nprob,
+                       pq_plan_info *info);
 
 /* Gray digits (reference digit order, one per row after the split, i.e. R
  * entries for digits 0..R-1 of the split problem) that the GPU path assigns

@@ -99,6 +99,8 @@ SIGNATURES = [
     ("pq_perm_finish", ctypes.c_int, [c_double_p, ctypes.c_int, c_double_p]),
     ("pq_perm_plan", ctypes.c_int,
      [ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, ctypes.POINTER(PlanInfo)]),
+    ("pq_perm_batch_plan", ctypes.c_int,
+     [ctypes.c_int, ctypes.c_int, c_int32_p, c_int32_p, ctypes.c_int, ctypes.POINTER(PlanInfo)]),
     ("pq_perm_gray_of_offset", ctypes.c_int,
      [ctypes.c_int, c_int32_p, ctypes.c_int64, c_int32_p]),
     ("pq_perm_segment_sums_c128", ctypes.c_int,

@@ -1017,6 +1017,58 @@ int perm_wide_locked(const double *A, int R, int C, const int32_t *rows, const i
 }
 } // namespace pqperm
 
+extern "C" int pq_perm_batch_plan(int R, int C, const int32_t *rows, const int32_t *cols,
+                                  int nprob, pq_plan_info *info)
+{
+    if (!info || R < 0 || C < 0 || nprob < 1 || (R > 0 && !rows) || (C > 0 && !cols))
+        return fail(PQ_ERR_BAD_ARG, "bad batch plan arguments");
+    std::memset(info, 0, sizeof(*info));
+    LapShape sh;
+    std::string err;
+    int rc = lap_shape(R, C, rows, cols, sh, err);
+    if (rc)
+        return fail(rc, err);
+    long long sc = 0;
+    for (int j = 0; j < C; j++)
+        sc += cols[j];
+    if (sh.sum_rows != sc)
+        return fail(PQ_ERR_SUM_MISMATCH, "Number of input and output states should be equal");
+    info->sum_rows = sh.sum_rows;
+    info->idx_max = 1;
+    info->seg_len = 1;
+    info->nseg = 1;
+    if (sh.trivial) {
+        info->trivial = 1;
+        return PQ_OK;
+    }
+    // the same steps as perm_batch_locked's planner
+    static const bool use_hyper = [] {
+        const char *e = std::getenv("PQ_PERM_HYPER");
+        return e ? std::atoi(e) != 0 : true;
+    }();
+    lap_expand_columns(sh);
+    const LapVariant v = perm_variant(sh.NC);
+    const bool hyper = use_hyper && lap_make_hyper(sh);
+    if (lap_smem_bytes(sh.D, v.S, v.NCL, true) > kLapSmemLimit)
+        return fail(PQ_ERR_TOO_LARGE, kLapTooWide);
+    const int min_segs_fill =
+        (int)std::min<long long>(1 << 20, (3LL * 148 * kLapThreads) / nprob);
+    LapProblem q;
+    LapWide w;
+    lap_fill(sh, v.S * v.NCL, q, v.S == 32 ? &w : nullptr,
+             std::max(kLapThreads / v.S, min_segs_fill));
+    info->seg_len = q.W;
+    info->nseg = q.nseg;
+    info->idx_max = (int64_t)q.W * q.nseg;
+    info->active_rows = sh.D;
+    info->active_cols = sh.NC;
+    info->low_digits = q.q;
+    info->kernel = hyper ? 4 : 3;
+    info->cols_padded = v.S * v.NCL;
+    info->flops_per_term = 2.0 * sh.NC + 6.0 * sh.M + 2.0;
+    return PQ_OK;
+}
+
 extern "C" int pq_perm_batch_c128(const double *A, int R, int C, int nprob,
                                   const int32_t *row_mult, const int32_t *col_mult,
                                   double *out)

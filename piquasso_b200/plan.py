@@ -29,6 +29,19 @@ def plan(rows, cols):
     return {name: getattr(info, name) for name, _ in info._fields_}
 
 
+def batch_plan(rows, cols, nprob=1):
+    """Plan of ONE problem of a ``permanent_batch`` call of ``nprob`` problems
+    (``pq_perm_batch_plan``): ``kernel`` 3 = term-by-term batched walk, 4 = hypercube
+    flavour; ``cols_padded`` = columns after the column multiplicities were written out."""
+    lib = _lib.load()
+    r, c = _i32(rows), _i32(cols)
+    info = _lib.PlanInfo()
+    _lib.check(lib.pq_perm_batch_plan(len(r), len(c), r.ctypes.data_as(_lib.c_int32_p),
+                                      c.ctypes.data_as(_lib.c_int32_p), int(nprob),
+                                      ctypes.byref(info)))
+    return {name: getattr(info, name) for name, _ in info._fields_}
+
+
 def gray_of_offset(rows, offset):
     """Gray digits (reference digit order, one per row) the GPU path assigns to
     ``offset``: enumeration parity with src/n_aryGrayCodeCounter.hpp:170-194."""

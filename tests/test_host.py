@@ -423,3 +423,45 @@ def test_bulk_pcg64_streams_equal_numpy_bit_generators(lib):
     rng = np.random.default_rng(7 + 2)
     for _ in range(20):
         assert s.random(np.array([2]))[0] == rng.random()
+
+
+def test_batch_plan_flavours_and_term_counts():
+    """Planner of pq_perm_batch_c128 (no GPU): the hypercube flavour needs unit columns
+    (after the column multiplicities were written out) and three rows of multiplicity 1
+    after the split; it always keeps those three digits low (segments are multiples of 8
+    terms); segments tile the term space exactly; column multiplicities that do not fit
+    32 unit columns keep the general flavour."""
+    from piquasso_b200 import plan as pqplan
+    rng = np.random.default_rng(11)
+    seen = set()
+    for trial in range(300):
+        d = int(rng.integers(3, 40))
+        n = int(rng.integers(1, 45))
+        rows = rng.multinomial(n, np.ones(d) / d)
+        k = int(rng.integers(1, d + 1))
+        cols = np.zeros(d, dtype=int)
+        cols[rng.choice(d, k, replace=False)] = rng.multinomial(n, np.ones(k) / k)
+        nprob = int(rng.choice([1, 10, 1000, 100000]))
+        p = pqplan.batch_plan(rows, cols, nprob)
+        # reference term count: prod(r_i + 1) after the split (src/permanent.cpp:131-142)
+        r = rows[rows > 0].copy()
+        r[np.argmin(r)] -= 1
+        idx_max = int(np.prod(r + 1, dtype=object))
+        assert p["idx_max"] == idx_max and p["seg_len"] * p["nseg"] == idx_max
+        nc, m = int(np.count_nonzero(cols)), int(cols.sum())
+        unit_after = m <= 32
+        ones = int(np.count_nonzero(r == 1))
+        width = m if unit_after else nc
+        want_hyper = unit_after and ones >= 3 and 4 <= width <= 32
+        assert (p["kernel"] == 4) == want_hyper, (rows, cols, p)
+        assert p["active_cols"] == width
+        if p["kernel"] == 4:
+            assert p["seg_len"] % 8 == 0 and p["low_digits"] >= 3
+        if nc <= 32:
+            assert p["cols_padded"] == width       # one lane per segment, no padding
+        seen.add((p["kernel"], unit_after))
+    assert {(3, True), (4, True), (3, False)} <= seen
+    # early-outs and errors as for the single permanent (src/permanent.cpp:97-108)
+    assert pqplan.batch_plan([0, 0], [0, 0])["trivial"] == 1
+    with pytest.raises(RuntimeError):
+        pqplan.batch_plan([1, 0], [1, 1])
