@@ -501,7 +501,9 @@ def test_permanent_batch_and_detection_probabilities():
     outs = [o for o in itertools.product(range(4), repeat=d) if sum(o) == 3]
     p = detection_probabilities(u, inp, outs)
     assert len(outs) == 35 and abs(p.sum() - 1.0) < 1e-12
-    # golden values of the reference's tests (tests/_simulators/passive/test_preparations.py:231-282)
+    # (the reference's golden probabilities, tests/_simulators/passive/test_preparations.py:231-282,
+    # run through this entry in test_gpu_envelope.py::test_detection_probabilities_reference_goldens)
+    # a sum mismatch in any problem fails the call like the single permanent (src/permanent.cpp:97-104)
     with pytest.raises(RuntimeError):
         permanent_batch(u, [[1, 0, 0, 0, 0]], [[1, 1, 0, 0, 0]])
 
