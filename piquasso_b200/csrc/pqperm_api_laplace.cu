@@ -205,7 +205,15 @@ void lap_fill(const LapShape &sh, int ncp, LapProblem &q, LapWide *wide = nullpt
     for (int d = 0; d < sh.D; d++)
         total *= (sh.mult[d] + 1);
     int seglen = total >= kLapBigProblem ? kLapSegLenBig : kLapSegLen;
-    if (sh.hyper && total >= kLapBigProblem) {
+    // batched permanents (min_segs > 1): the segment count is bounded from below anyway, so
+    // mid-size problems take the long segments too (a seed costs ~20 terms of a 16-column walk)
+    static const bool long_small = [] {
+        const char *e = std::getenv("PQ_BATCH_LONG_SEGS");
+        return e ? std::atoi(e) != 0 : true;
+    }();
+    if (min_segs > 1 && long_small)
+        seglen = kLapSegLenBig;
+    if (sh.hyper && (total >= kLapBigProblem || (min_segs > 1 && long_small))) {
         // the hypercube flavour tabulates BLOCKS of 8 terms: up to 8 x 256 terms per segment
         // (B200 sweep, n = 24 batches: 256 terms 10.6 ms, 512 10.2, 1024 10.1, 2048 10.2;
         // n = 20: 8.14 / 8.09 / 8.19 / 8.87)
