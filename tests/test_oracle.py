@@ -176,6 +176,27 @@ def test_job_count_does_not_change_the_sum():
     assert relerr(whole[0] / 2 ** 8, vals[0]) < 1e-12
 
 
+def test_digit_order_does_not_change_the_sum():
+    """The sum runs over ALL Gray tuples, so it does not depend on the order of the rows
+    (= digits): what the batched hypercube flavour relies on when it moves three rows of
+    multiplicity 1 to the lowest digits (piquasso_b200/csrc/pqperm_permhyper.cuh).  Checked
+    on the reference's algorithm itself, with repeated rows and columns."""
+    rng = np.random.default_rng(17)
+    for trial in range(12):
+        d = int(rng.integers(4, 9))
+        nph = int(rng.integers(3, 10))
+        rows = rng.multinomial(nph, np.ones(d) / d)
+        cols = rng.multinomial(nph, np.ones(d) / d)
+        a = haar(d, 700 + trial)
+        base = oracle.permanent(a, rows, cols, precision=1)
+        perm = rng.permutation(d)
+        moved = oracle.permanent(a[perm], rows[perm], cols, precision=1)
+        assert abs(moved - base) <= 1e-13 * abs(base) + 1e-18, (rows, cols, perm)
+        if oracle.ref_available():
+            ref = oracle.ref_permanent(np.ascontiguousarray(a[perm]), rows[perm], cols)
+            assert abs(ref - base) <= 1e-10 * abs(base) + 1e-16
+
+
 def test_compiled_reference_when_present():
     """Where oracle/_ref exists (it travels to the GPU box) the restatement and
     the unmodified reference agree to the last bits on fresh random inputs."""
