@@ -30,7 +30,7 @@ namespace {
 // ~10 % at 64 terms; long segments are used where the problem still yields
 // thousands of them (measured: k=25 walk 0.465 -> 0.388 ms).
 constexpr int kLapSegLen = 64;
-constexpr int kLapSegLenBig = kLapMaxSegLen;          // 256
+constexpr int kLapSegLenBig = kLapMaxSegLen;          // 512
 constexpr long long kLapBigProblem = 1LL << 18;       // terms
 // the sampler step plans its shots on up to this many host threads ...
 constexpr int kPlanThreadsMax = 8;

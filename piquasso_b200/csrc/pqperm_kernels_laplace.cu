@@ -27,8 +27,8 @@ static cudaError_t launch_one(const LapParams &P, int total_blocks, size_t smem,
                               cudaStream_t stream)
 {
     auto kernel = laplace_walk_kernel<NCL, S, PQ_LAP_UNIT != 0, PQ_LAP_MODE>;
-    // static (step tables, ~4.1 KB) + dynamic shared memory above 48 KB needs the opt-in
-    if (smem + 6 * 1024 > 48 * 1024) {
+    // static (step tables) + dynamic shared memory above 48 KB needs the opt-in
+    if (smem + kLapStaticSmem + 1024 > 48 * 1024) {
         static std::mutex mu;
         static std::map<int, size_t> raised; // device -> largest limit set
         int dev = 0;

@@ -13,8 +13,8 @@ static cudaError_t launch_hyper_nc(const LapParams &P, int total_blocks, size_t 
                                    cudaStream_t stream)
 {
     auto kernel = perm_hyper_kernel<NC>;
-    // static (step tables, ~4.1 KB) + dynamic shared memory above 48 KB needs the opt-in
-    if (smem + 6 * 1024 > 48 * 1024) {
+    // static (step tables) + dynamic shared memory above 48 KB needs the opt-in
+    if (smem + kLapStaticSmem + 1024 > 48 * 1024) {
         static std::mutex mu;
         static std::map<int, size_t> raised; // device -> largest limit set
         int dev = 0;

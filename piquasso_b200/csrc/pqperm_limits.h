@@ -26,15 +26,24 @@ constexpr int kBinMinDigitsAuto = 23;
 constexpr int64_t kMaxSegLenBinary = INT64_C(1) << 14;
 constexpr int64_t kMaxSegLenNary = INT64_C(1) << 10;  // step tables live in shared memory (9 KB)
 
-constexpr int kLapMaxSegLen = 256;     // Laplace: terms per segment (tables in shared memory)
+// Laplace: terms per segment (step tables in shared memory, 16 bytes per term).  B200,
+// batches of 2000 k-column problems, 256 -> 512 -> 1024 terms: k = 24 197.7 -> 188.0 -> 186.6 ms,
+// k = 25 409.0 -> 402.2 -> 398.2 ms; config 4 (10^4 shots) kernels 1.285 -> 1.257 s at 512.
+#ifndef PQ_LAP_MAXSEG
+#define PQ_LAP_MAXSEG 512
+#endif
+constexpr int kLapMaxSegLen = PQ_LAP_MAXSEG;
+// static shared memory of the batched walks: the two step tables and a few words
+constexpr size_t kLapStaticSmem = (size_t)kLapMaxSegLen * 16 + 64;
 #ifndef PQ_LAP_THREADS
 #define PQ_LAP_THREADS 128
 #endif
 constexpr int kLapThreads = PQ_LAP_THREADS;
 // Dynamic shared memory of one CTA of the Laplace walk: the (D+1) x NCP complex
 // matrix, then every thread's double-double totals (4 doubles per column of the
-// lane plus 4 for the full product).  Must fit beside ~2.3 KB of static tables.
-constexpr size_t kLapSmemLimit = 224 * 1024;
+// lane plus 4 for the full product).  Must fit the 227 KB of a B200 CTA beside the
+// static tables (and 1 KB the driver reserves).
+constexpr size_t kLapSmemLimit = 227 * 1024 - kLapStaticSmem - 1024;
 // (perm_only: batched permanents keep only the full product's four slots)
 inline size_t lap_smem_bytes(int D, int S, int NCL, bool perm_only = false)
 {
