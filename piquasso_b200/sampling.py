@@ -120,13 +120,29 @@ def detection_probabilities(interferometer, input, outputs):
     ``|permanent(U, rows=output, cols=input)|^2 / (prod output! * prod input!)``
     (``piquasso/_simulators/passive/probabilities.py:26-54`` and
     ``utils.py:131-138`` of the reference), all outputs in one batched call."""
-    from scipy.special import factorial
-
     outputs = np.atleast_2d(np.asarray(outputs, dtype=int))
     input = np.asarray(input, dtype=int)
     amps = permanent_batch(interferometer, outputs, input)
-    norm = np.prod(factorial(outputs), axis=1) * np.prod(factorial(input))
+    norm = np.prod(_factorials(outputs), axis=1) * np.prod(_factorials(input))
     return np.abs(amps) ** 2 / norm
+
+
+_FACTORIAL_TABLE = None
+
+
+def _factorials(occupations):
+    """``scipy.special.factorial`` of an occupation array through a table of its own
+    values (0! .. 170!, the same doubles): the element-wise scipy call was half the wall
+    time of a 2000-output probability table (3 ms of 6.5)."""
+    from scipy.special import factorial
+
+    global _FACTORIAL_TABLE
+    if _FACTORIAL_TABLE is None:
+        _FACTORIAL_TABLE = factorial(np.arange(171))
+    occupations = np.asarray(occupations)
+    if occupations.size and (occupations.min() < 0 or occupations.max() > 170):
+        return factorial(occupations)
+    return _FACTORIAL_TABLE[occupations]
 
 
 def grad_perm(matrix, rows, cols):

@@ -465,3 +465,12 @@ def test_batch_plan_flavours_and_term_counts():
     assert pqplan.batch_plan([0, 0], [0, 0])["trivial"] == 1
     with pytest.raises(RuntimeError):
         pqplan.batch_plan([1, 0], [1, 1])
+
+
+def test_factorial_table_equals_scipy():
+    from scipy.special import factorial
+    from piquasso_b200.sampling import _factorials
+    occ = np.random.default_rng(1).integers(0, 40, size=(64, 9))
+    assert np.array_equal(_factorials(occ), factorial(occ))
+    big = np.array([0, 170, 171, 200])
+    assert np.array_equal(_factorials(big), factorial(big))
