@@ -425,9 +425,14 @@ def generate_samples(input, shots, interferometer, seed_sequence, reject_conditi
             modes = shrink[live, ridx]
             current_input[live, modes] += 1
             if n > 1:
-                shifted = np.where(cols[None, : n - 1] >= ridx[:, None],
-                                   shrink[live, 1:], shrink[live, : n - 1])
-                shrink[live, : n - 1] = shifted
+                if live.size == nb:
+                    # no rejected shot: plain slices instead of two gathered copies
+                    np.copyto(shrink[:, : n - 1], shrink[:, 1:],
+                              where=cols[None, : n - 1] >= ridx[:, None])
+                else:
+                    shifted = np.where(cols[None, : n - 1] >= ridx[:, None],
+                                       shrink[live, 1:], shrink[live, : n - 1])
+                    shrink[live, : n - 1] = shifted
             remaining[live] -= 1
             _tick("host: grow input", t0)
             t0 = time.perf_counter()
